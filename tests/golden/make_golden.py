@@ -1,0 +1,131 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Outputs (small, committed): tests/golden/*.pt
+  c1_fp32.pt   BASELINE config 1 (B=4, C=10, n_ctx=2, depth=9), fp32-ref oracle definition
+               (SURVEY.md §8c): eval logits, train loss, features, every parameter gradient of the
+               reference's own autograd (full tensors < 64k elems, strided sample + norm otherwise).
+  c1_fp16_logits.pt  the reference as-is (PREC=fp16) eval logits, for information.
+  c3s_fp32.pt  C=38 classes / B=2, same content (text-heavy shape of config 3).
+  fedavg.pt    MaPLeFederated.safe_average_weights / check_weights_valid known answers at
+               K = 2, 3, 8, 16, 17, 32, 33 incl. NaN/Inf entries.
+Inputs are regenerated from seeds by federated_multi_modal_b200.synth on any box.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+
+from federated_multi_modal_b200 import synth  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+BIG = 65536
+STRIDE = 97
+
+
+def pack_grad(g: torch.Tensor):
+    g = g.detach().float()
+    if g.numel() <= BIG:
+        return dict(full=g.clone())
+    flat = g.reshape(-1)
+    return dict(sample=flat[::STRIDE].clone(), stride=STRIDE, norm=flat.double().norm().item(),
+                sum=flat.double().sum().item(), shape=tuple(g.shape))
+
+
+def run_case(B, C, seed_clip=0, seed_pl=1, seed_batch=123, fp32=True):
+    torch.manual_seed(0)
+    cfg = synth.make_cfg()
+    names = synth.synthetic_classnames(C)
+    sd = synth.random_clip_state_dict(seed_clip)
+    pl = synth.random_prompt_learner_state(seed_pl)
+    model = rh.build_reference_customclip(sd, names, cfg, pl, fp32=fp32)
+    img, lab = synth.make_batch(B, C, seed_batch)
+    out = dict(meta=dict(B=B, C=C, seed_clip=seed_clip, seed_pl=seed_pl, seed_batch=seed_batch,
+                         n_ctx=2, depth=9, fp32=fp32, torch=torch.__version__))
+    model.eval()
+    feats = {}
+    with torch.no_grad():
+        out["logits_eval"] = model(img if fp32 else img.half()).float().clone()
+    if not fp32:
+        return out, model
+    # features through the reference's own sub-modules
+    with torch.no_grad():
+        prompts, shared, dtx, dvs = model.prompt_learner()
+        out["text_features"] = model.text_encoder(prompts, model.tokenized_prompts, dtx).clone()
+        out["image_features"] = model.image_encoder(img, shared, dvs, None).clone()
+        out["shared_ctx"] = shared.clone()
+    # per-block activations via forward hooks on the reference modules (batch-major)
+    acts = {}
+    hooks = []
+    for tower, blocks in (("vis", model.image_encoder.transformer.resblocks),
+                          ("txt", model.text_encoder.transformer.resblocks)):
+        for li in (0, 1, 8, 11):
+            def mk(name):
+                def hook(mod, inp, outp):
+                    x = outp[0].detach().permute(1, 0, 2)  # LND -> NLD
+                    acts[name] = x[:2, ::16, ::8].clone()  # small strided sample
+                return hook
+            hooks.append(blocks[li].register_forward_hook(mk(f"{tower}{li}")))
+    model.train()
+    loss = model(img, lab)
+    for h in hooks:
+        h.remove()
+    model.zero_grad()
+    loss.backward()
+    out["loss"] = loss.detach().clone()
+    out["acts"] = acts
+    grads = {}
+    for n, p in model.named_parameters():
+        if p.requires_grad and p.grad is not None:
+            grads[n] = pack_grad(p.grad)
+    out["grads"] = grads
+    out["n_trainable"] = sum(1 for p in model.parameters() if p.requires_grad)
+    out["n_with_grad"] = len(grads)
+    out["n_state_dict_keys"] = len(model.state_dict())
+    return out, model
+
+
+def fedavg_cases():
+    _, _, fed = rh.load_reference()
+    g = torch.Generator().manual_seed(7)
+    cases = {}
+    for K in (2, 3, 8, 16, 17, 32, 33):
+        dicts = []
+        for k in range(K):
+            a = torch.randn(1000, generator=g)
+            b = (torch.randn(33, 7, generator=g) * 3).half()
+            if k == 1:
+                a[3] = float("nan"); a[4] = float("inf"); a[5] = float("-inf")
+            dicts.append({"a": a, "b": b, "s": torch.tensor(2.6592600 + 0.001 * k)})
+        avg = fed.MaPLeFederated.safe_average_weights(None, dicts, K)
+        cases[K] = dict(inputs=dicts, out={k: v.clone() for k, v in avg.items()},
+                        fp32_mean={k: torch.nan_to_num(torch.stack([d[k].float() for d in dicts]), nan=0.0,
+                                                       posinf=1e4, neginf=-1e4).mean(0) for k in dicts[0]},
+                        valid=[bool(fed.MaPLeFederated.check_weights_valid(None, d)) for d in dicts])
+    return cases
+
+
+if __name__ == "__main__":
+    import contextlib, io
+    torch.set_num_threads(8)
+    o, _ = run_case(4, 10)
+    torch.save(o, os.path.join(HERE, "c1_fp32.pt"))
+    print("c1 loss", o["loss"].item(), "grads", o["n_with_grad"], "/", o["n_trainable"])
+    o16, _ = run_case(4, 10, fp32=False)
+    torch.save(o16, os.path.join(HERE, "c1_fp16_logits.pt"))
+    rel = ((o16["logits_eval"] - o["logits_eval"]).abs().max() / o["logits_eval"].abs().max()).item()
+    print("fp16-ref vs fp32-ref max rel logit err", rel)
+    o3, _ = run_case(2, 38, seed_batch=321)
+    torch.save(o3, os.path.join(HERE, "c3s_fp32.pt"))
+    print("c3s loss", o3["loss"].item())
+    with contextlib.redirect_stdout(io.StringIO()):
+        fc = fedavg_cases()
+    torch.save(fc, os.path.join(HERE, "fedavg.pt"))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
