@@ -1,0 +1,97 @@
+"""ctypes binding of libmfk.so (the C ABI declared in include/mfk.h).
+
+There is NO fallback: if the shared library is missing it is built with nvcc; if that fails, or a
+kernel returns a non-zero status, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmfk.so")
+
+P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+# name -> argument ctypes (return type is int unless listed in _RET)
+SIGNATURES = {
+    "mfk_version": [],
+    "mfk_error_string": [I],
+    "mfk_gemm_bf16": [P, L, P, L, I, I, I, P, I, P, L, P, L, P, L, P, L, P, L, I, P],
+    "mfk_attn_fwd": [P, P, P, I, I, I, I, P],
+    "mfk_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P],
+    "mfk_layernorm_fwd": [P, P, P, P, P, P, P, P, P, I, I, F, P],
+    "mfk_ln_bwd_ctas": [I],
+    "mfk_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+    "mfk_colsum": [P, I, L, I, I, P, P, I, P],
+    "mfk_patch_im2col": [P, P, I, I, P],
+    "mfk_vis_assemble_lnpre": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, P],
+    "mfk_text_assemble": [P, P, P, P, P, I, I, I, I, I, P],
+    "mfk_prompt_splice_fwd": [P, P, I, I, I, I, I, P],
+    "mfk_prompt_splice_bwd": [P, P, P, I, I, I, I, I, I, I, P],
+    "mfk_scatter_rows": [P, P, P, P, I, I, P],
+    "mfk_transpose_bf16": [P, I, L, P, L, P, L, I, I, P],
+    "mfk_cast_f32_bf16": [P, P, L, P],
+    "mfk_linear_small_fwd": [P, P, P, P, I, I, I, P],
+    "mfk_linear_small_bwd": [P, P, P, P, P, P, P, I, I, I, P],
+    "mfk_head_workspace_floats": [I, I, I],
+    "mfk_head_forward_backward": [P, P, P, P, P, P, P, P, P, I, I, I, P],
+    "mfk_fedavg_reduce": [P, P, F, I, L, I, P, P, P, P],
+    "mfk_check_finite": [P, L, I, P, P],
+    "mfk_grad_norm": [P, L, P, P, P],
+    "mfk_sgd_step": [P, P, P, L, P, P, P],
+}
+_RET = {"mfk_error_string": ctypes.c_char_p, "mfk_head_workspace_floats": L}
+_NO_STATUS = {"mfk_version", "mfk_error_string", "mfk_head_workspace_floats", "mfk_ln_bwd_ctas"}
+
+_lock = threading.Lock()
+_lib = None
+launch_count = 0  # number of C-ABI kernel-launching calls made (bench.py reports it)
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"{LIB_PATH} is missing: run `python -m federated_multi_modal_b200.csrc.build`")
+            from .csrc.build import build
+            build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.argtypes = args
+            fn.restype = _RET.get(name, I)
+        _lib = lib
+        return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke a C-ABI entry point; tensors are passed as raw pointers. Raises on non-zero status."""
+    global launch_count
+    lib = load()
+    conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
+    rc = getattr(lib, name)(*conv)
+    if name in _NO_STATUS:
+        return rc
+    launch_count += 1
+    if rc != 0:
+        msg = lib.mfk_error_string(rc)
+        raise RuntimeError(f"{name} failed with status {rc}: {msg.decode() if msg else '?'}")
+    return 0

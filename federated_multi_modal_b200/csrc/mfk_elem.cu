@@ -1,0 +1,538 @@
+// Warp-level LayerNorm, prompt splice, token assembly, im2col, transposes and small fp32 linears
+// for the MaPLe towers (HBM-bound kernels; SURVEY.md §2.2 K2,K3,K9,K10,K11,K12,K13).
+#include "mfk_common.cuh"
+#include "../../include/mfk.h"
+
+namespace {
+using namespace mfk;
+
+constexpr int kLnWarps = 8;
+
+// ============================================================================ LayerNorm forward
+// clip/model.py:153-159: fp32 LayerNorm (eps 1e-5, biased variance). One warp per row,
+// VEC float4 per lane (D = 128*VEC), two-pass statistics held in registers.
+template <int VEC>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[VEC], float& mean, float& rstd, float eps) {
+  constexpr float invD = 1.0f / (128.0f * VEC);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) * invD;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  rstd = rsqrtf(warp_sum(q) * invD + eps);
+}
+
+template <int VEC>
+__device__ __forceinline__ void ln_row_write(const float4 (&v)[VEC], float mean, float rstd, const float* gamma,
+                                             const float* beta, bf16* y16, float* y32, int lane) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y32) reinterpret_cast<float4*>(y32)[c4] = o;
+    if (y16) reinterpret_cast<uint2*>(y16)[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ rowidx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, bf16* __restrict__ y16, float* __restrict__ y32,
+              float* __restrict__ xsave, float* __restrict__ mean_o, float* __restrict__ rstd_o, int M, float eps) {
+  constexpr int D = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const size_t src = rowidx ? (size_t)rowidx[row] : (size_t)row;
+  const float4* xr = reinterpret_cast<const float4*>(x + src * D);
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = xr[lane + 32 * i];
+  if (xsave) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) reinterpret_cast<float4*>(xsave + (size_t)row * D)[lane + 32 * i] = v[i];
+  }
+  float mean, rstd;
+  ln_row_stats<VEC>(v, mean, rstd, eps);
+  if (lane == 0) {
+    if (mean_o) mean_o[row] = mean;
+    if (rstd_o) rstd_o[row] = rstd;
+  }
+  ln_row_write<VEC>(v, mean, rstd, gamma, beta, y16 ? y16 + (size_t)row * D : nullptr,
+                    y32 ? y32 + (size_t)row * D : nullptr, lane);
+}
+
+// ============================================================================ LayerNorm backward
+// dx = rstd * (dy*g - mean_D(dy*g) - xhat * mean_D(dy*g*xhat));  g_out = g_in + dx.
+// dgamma/dbeta: per-CTA partial column sums (deterministic two-stage reduction).
+template <int VEC, bool DY_BF16>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ mean_i,
+              const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* g_in,
+              float* g_out, bf16* __restrict__ g16, float* __restrict__ partial, int M) {
+  constexpr int D = 128 * VEC;
+  __shared__ __align__(16) float red[kLnWarps][D];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float4 dg[VEC], db[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gam[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+
+  for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+    const float mean = mean_i[row], rstd = rstd_i[row];
+    float4 xh[VEC], d[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c4 = lane + 32 * i;
+      float4 xv = reinterpret_cast<const float4*>(x + (size_t)row * D)[c4];
+      if (DY_BF16) {
+        uint2 u = reinterpret_cast<const uint2*>(static_cast<const bf16*>(dy_) + (size_t)row * D)[c4];
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        d[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        d[i] = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + (size_t)row * D)[c4];
+      }
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y; dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
+      db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+      d[i].x *= gam[i].x; d[i].y *= gam[i].y; d[i].z *= gam[i].z; d[i].w *= gam[i].w;
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c4 = lane + 32 * i;
+      float4 o;
+      o.x = (d[i].x - s1 - xh[i].x * s2) * rstd;
+      o.y = (d[i].y - s1 - xh[i].y * s2) * rstd;
+      o.z = (d[i].z - s1 - xh[i].z * s2) * rstd;
+      o.w = (d[i].w - s1 - xh[i].w * s2) * rstd;
+      if (g_in) {
+        float4 r = reinterpret_cast<const float4*>(g_in + (size_t)row * D)[c4];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(g_out + (size_t)row * D)[c4] = o;
+      if (g16) reinterpret_cast<uint2*>(g16 + (size_t)row * D)[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+  if (!partial) return;
+  // cross-warp reduction of the per-lane column partials (fixed order over warps)
+  float* pg = partial + (size_t)blockIdx.x * 2 * D;
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      reinterpret_cast<float4*>(&red[warp][0])[lane + 32 * i] = half == 0 ? dg[i] : db[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += kLnWarps * 32) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnWarps; ++w) a += red[w][c];
+      pg[half * D + c] = a;
+    }
+  }
+}
+
+// out[c] (+)= sum_p partial[p, c]  (fixed order p = 0..P-1)
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int P, int N, long long pstride,
+                                      float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += partial[(size_t)p * pstride + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// ============================================================================ column sums (bias grads)
+template <bool IN_BF16>
+__global__ void colsum_partial_kernel(const void* __restrict__ x_, long long ld, int M, int N,
+                                      float* __restrict__ partial) {
+  // block (32, 8): 64 columns per block.x, rows strided by 8*gridDim.y
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  __shared__ float red[8][64];
+  float a = 0.f, b = 0.f;
+  if (c < N) {
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += gridDim.y * 8) {
+      if (IN_BF16) {
+        uint32_t u = *reinterpret_cast<const uint32_t*>(static_cast<const bf16*>(x_) + (size_t)r * ld + c);
+        float2 f = unpack_bf16(u);
+        a += f.x; b += f.y;
+      } else {
+        float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(x_) + (size_t)r * ld + c);
+        a += f.x; b += f.y;
+      }
+    }
+  }
+  red[threadIdx.y][threadIdx.x * 2] = a;
+  red[threadIdx.y][threadIdx.x * 2 + 1] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s0 += red[w][threadIdx.x * 2]; s1 += red[w][threadIdx.x * 2 + 1]; }
+    partial[(size_t)blockIdx.y * N + c] = s0;
+    partial[(size_t)blockIdx.y * N + c + 1] = s1;
+  }
+}
+
+// ============================================================================ im2col for conv1 16x16/s16
+// clip/model.py:514-518: conv(3->768, k=16, s=16, no bias) == [B*196, 768] x [768, 768]^T with
+// K index = c*256 + ky*16 + kx, patch p = gy*14 + gx.
+__global__ void im2col16_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int S) {
+  const int G = S / 16;
+  const int patch = blockIdx.x;             // b*G*G + gy*G + gx
+  const int b = patch / (G * G), pp = patch % (G * G), gy = pp / G, gx = pp % G;
+  // 768 K-values = 3 channels x 16 rows x 16 px; thread handles 4 consecutive px
+  for (int t = threadIdx.x; t < 192; t += blockDim.x) {
+    const int c = t / 64, ky = (t % 64) / 4, kx = (t % 4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * S + gy * 16 + ky) * S + gx * 16 + kx);
+    *reinterpret_cast<uint2*>(out + (size_t)patch * 768 + c * 256 + ky * 16 + kx) =
+        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// ============================================================================ vision token assembly + ln_pre
+// clip/model.py:522-544: [cls+pos0 ; patches+pos ; q16(shared_ctx)] -> ln_pre. One warp per token row.
+template <int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+vis_assemble_kernel(const float* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos,
+                    const float* __restrict__ shared_ctx, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ x0, float* __restrict__ x,
+                    float* __restrict__ mean_o, float* __restrict__ rstd_o, int B, int T, int n_ctx, float eps) {
+  constexpr int D = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= B * T) return;
+  const int b = row / T, t = row % T;
+  const int P = T - n_ctx - 1;  // patches
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + 32 * i;
+    if (t == 0) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(cls) + c4), p = __ldg(reinterpret_cast<const float4*>(pos) + c4);
+      v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    } else if (t <= P) {
+      float4 a = reinterpret_cast<const float4*>(tok + ((size_t)b * P + (t - 1)) * D)[c4];
+      float4 p = __ldg(reinterpret_cast<const float4*>(pos + (size_t)t * D) + c4);
+      v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    } else {
+      float4 a = __ldg(reinterpret_cast<const float4*>(shared_ctx + (size_t)(t - P - 1) * D) + c4);
+      v[i] = make_float4(q16(a.x), q16(a.y), q16(a.z), q16(a.w));
+    }
+    if (x0) reinterpret_cast<float4*>(x0 + (size_t)row * D)[c4] = v[i];
+  }
+  float mean, rstd;
+  ln_row_stats<VEC>(v, mean, rstd, eps);
+  if (lane == 0) {
+    if (mean_o) mean_o[row] = mean;
+    if (rstd_o) rstd_o[row] = rstd;
+  }
+  ln_row_write<VEC>(v, mean, rstd, gamma, beta, nullptr, x + (size_t)row * D, lane);
+}
+
+// ============================================================================ text prompt assembly
+// trainers/maple.py:157-166,181-187,54: cat(prefix, ctx, suffix) + positional_embedding, truncated to Te rows.
+__global__ void text_assemble_kernel(const float* __restrict__ prefix, const float* __restrict__ ctx,
+                                     const float* __restrict__ suffix, const float* __restrict__ pos,
+                                     float* __restrict__ x, int C, int Te, int n_ctx, int Tfull, int D) {
+  const int row = blockIdx.x;  // c*Te + t
+  const int c = row / Te, t = row % Te;
+  const float* src;
+  if (t == 0) src = prefix + (size_t)c * D;
+  else if (t <= n_ctx) src = ctx + (size_t)(t - 1) * D;
+  else src = suffix + ((size_t)c * (Tfull - 1 - n_ctx) + (t - 1 - n_ctx)) * D;
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(src) + i);
+    float4 p = __ldg(reinterpret_cast<const float4*>(pos + (size_t)t * D) + i);
+    reinterpret_cast<float4*>(x + (size_t)row * D)[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+}
+
+// ============================================================================ deep prompt splice
+// clip/model.py:320-349: overwrite n_ctx rows of every sequence with q16(prompt).
+__global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict__ prompt, int T, int row0, int n_ctx,
+                                  int D) {
+  const int b = blockIdx.x / n_ctx, j = blockIdx.x % n_ctx;
+  float* dst = x + ((size_t)b * T + row0 + j) * D;
+  const float* src = prompt + (size_t)j * D;
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(src) + i);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(q16(a.x), q16(a.y), q16(a.z), q16(a.w));
+  }
+}
+// backward: dprompt[j,:] = sum_b q16?(g[b,row0+j,:]) in batch order; optionally zero those rows of g / g16.
+__global__ void splice_bwd_kernel(float* __restrict__ g, bf16* __restrict__ g16, float* __restrict__ dprompt, int N,
+                                  int T, int row0, int n_ctx, int D, int round16, int zero) {
+  const int j = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f;
+  for (int b = 0; b < N; ++b) {
+    const size_t idx = ((size_t)b * T + row0 + j) * D + c;
+    const float v = g[idx];
+    s += round16 ? q16(v) : v;
+    if (zero) {
+      g[idx] = 0.f;
+      if (g16) g16[idx] = __float2bfloat16_rn(0.f);
+    }
+  }
+  dprompt[(size_t)j * D + c] = s;
+}
+
+// g[rowidx[r], :] = dx[r, :] (+ bf16 copy); g must have been zero-filled.
+__global__ void scatter_rows_kernel(const float* __restrict__ dx, const int* __restrict__ rowidx,
+                                    float* __restrict__ g, bf16* __restrict__ g16, int D) {
+  const int r = blockIdx.x;
+  const size_t dst = (size_t)rowidx[r] * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const float v = dx[(size_t)r * D + i];
+    g[dst + i] = v;
+    if (g16) g16[dst + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ============================================================================ transposes / packing
+template <typename TIN>
+__global__ void transpose_to_bf16_kernel(const TIN* __restrict__ in, long long ldi, bf16* __restrict__ out,
+                                         long long ldo, bf16* __restrict__ copy, long long ldc, int M, int N) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = m0 + i, n = n0 + threadIdx.x;
+    float v = 0.f;
+    if (m < M && n < N) {
+      v = (float)in[(size_t)m * ldi + n];
+      if (copy) copy[(size_t)m * ldc + n] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, m = m0 + threadIdx.x;
+    if (n < N && m < M) out[(size_t)n * ldo + m] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  } else {
+    for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i]);
+  }
+}
+
+// ============================================================================ small fp32 linears (prompt learner)
+// trainers/maple.py:194-215: y[m,N] = x[m,K] W[N,K]^T + b, m = n_ctx (tiny). One warp per output column.
+__global__ void linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                        const float* __restrict__ b, float* __restrict__ y, int m, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  for (int r = 0; r < m; ++r) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += x[(size_t)r * K + k] * W[(size_t)n * K + k];
+    s = warp_sum(s);
+    if (lane == 0) y[(size_t)r * N + n] = s + (b ? b[n] : 0.f);
+  }
+}
+// dW[N,K] = dy^T x ; db[N] = sum_r dy ; dx[m,K] (+)= dy W
+__global__ void linear_small_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                          float* __restrict__ dW, float* __restrict__ db, int m, int N, int K) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < m; ++r) s += dy[(size_t)r * N + n] * x[(size_t)r * K + k];
+    dW[(size_t)n * K + k] = s;
+  }
+  if (threadIdx.x == 0 && db) {
+    float s = 0.f;
+    for (int r = 0; r < m; ++r) s += dy[(size_t)r * N + n];
+    db[n] = s;
+  }
+}
+__global__ void linear_small_bwd_x_kernel(const float* __restrict__ W, const float* __restrict__ dy,
+                                          const float* __restrict__ add, float* __restrict__ dx, int m, int N, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  for (int r = 0; r < m; ++r) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dy[(size_t)r * N + n] * W[(size_t)n * K + k];
+    dx[(size_t)r * K + k] = s + (add ? add[(size_t)r * K + k] : 0.f);
+  }
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int mfk_layernorm_fwd(const float* x, const int* rowidx, const float* gamma, const float* beta,
+                                 void* y_bf16, float* y_f32, float* x_save, float* mean, float* rstd, int M, int D,
+                                 float eps, void* stream) {
+  if (!x || !gamma || !beta || M <= 0) return MFK_EARG;
+  if (!y_bf16 && !y_f32) return MFK_EARG;
+  const int grid = (M + kLnWarps - 1) / kLnWarps;
+  bf16* y16 = static_cast<bf16*>(y_bf16);
+  if (D == 768) ln_fwd_kernel<6><<<grid, kLnWarps * 32, 0, ST(stream)>>>(x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  else if (D == 512) ln_fwd_kernel<4><<<grid, kLnWarps * 32, 0, ST(stream)>>>(x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  else if (D == 128) ln_fwd_kernel<1><<<grid, kLnWarps * 32, 0, ST(stream)>>>(x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  else return MFK_ESHAPE;
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_ln_bwd_ctas(int M) {
+  int g = (M + kLnWarps - 1) / kLnWarps;
+  return g < 296 ? g : 296;  // 2 CTAs per SM on 148 SMs
+}
+
+extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, const float* g_in, float* g_out, void* g_out_bf16,
+                                 float* dgamma, float* dbeta, float* partial_ws, int accumulate, int M, int D,
+                                 void* stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !g_out || M <= 0) return MFK_EARG;
+  if ((dgamma || dbeta) && !partial_ws) return MFK_EARG;
+  const int grid = mfk_ln_bwd_ctas(M);
+  bf16* g16 = static_cast<bf16*>(g_out_bf16);
+  float* part = (dgamma || dbeta) ? partial_ws : nullptr;
+#define LNB(V)                                                                                                     \
+  do {                                                                                                             \
+    if (dy_is_bf16) ln_bwd_kernel<V, true><<<grid, kLnWarps * 32, 0, ST(stream)>>>(dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M); \
+    else ln_bwd_kernel<V, false><<<grid, kLnWarps * 32, 0, ST(stream)>>>(dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M);           \
+  } while (0)
+  if (D == 768) LNB(6);
+  else if (D == 512) LNB(4);
+  else if (D == 128) LNB(1);
+  else return MFK_ESHAPE;
+#undef LNB
+  MFK_CHECK_LAUNCH();
+  if (part) {
+    const int tb = 128;
+    if (dgamma) partial_reduce_kernel<<<(D + tb - 1) / tb, tb, 0, ST(stream)>>>(part, grid, D, 2LL * D, dgamma, accumulate);
+    if (dbeta) partial_reduce_kernel<<<(D + tb - 1) / tb, tb, 0, ST(stream)>>>(part + D, grid, D, 2LL * D, dbeta, accumulate);
+    MFK_CHECK_LAUNCH();
+  }
+  return MFK_OK;
+}
+
+extern "C" int mfk_colsum(const void* x, int is_bf16, long long ld, int M, int N, float* out, float* partial_ws,
+                          int accumulate, void* stream) {
+  if (!x || !out || !partial_ws || M <= 0 || N <= 0 || (N & 1)) return MFK_EARG;
+  const int P = 32;
+  dim3 grid((N + 63) / 64, P), block(32, 8);
+  if (is_bf16) colsum_partial_kernel<true><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
+  else colsum_partial_kernel<false><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
+  partial_reduce_kernel<<<(N + 127) / 128, 128, 0, ST(stream)>>>(partial_ws, P, N, N, out, accumulate);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_patch_im2col(const float* img, void* out_bf16, int B, int S, void* stream) {
+  if (!img || !out_bf16 || B <= 0 || S % 16) return MFK_EARG;
+  const int G = S / 16;
+  im2col16_kernel<<<B * G * G, 192, 0, ST(stream)>>>(img, static_cast<bf16*>(out_bf16), B, S);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_vis_assemble_lnpre(const float* tok, const float* cls, const float* pos, const float* shared_ctx,
+                                      const float* gamma, const float* beta, float* x0_save, float* x, float* mean,
+                                      float* rstd, int B, int T, int n_ctx, int D, float eps, void* stream) {
+  if (!tok || !cls || !pos || !shared_ctx || !x || D != 768) return MFK_EARG;
+  const int M = B * T;
+  vis_assemble_kernel<6><<<(M + kLnWarps - 1) / kLnWarps, kLnWarps * 32, 0, ST(stream)>>>(
+      tok, cls, pos, shared_ctx, gamma, beta, x0_save, x, mean, rstd, B, T, n_ctx, eps);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_text_assemble(const float* prefix, const float* ctx, const float* suffix, const float* pos,
+                                 float* x, int C, int Te, int n_ctx, int Tfull, int D, void* stream) {
+  if (!prefix || !ctx || !suffix || !pos || !x || Te > Tfull || D % 4) return MFK_EARG;
+  text_assemble_kernel<<<C * Te, 128, 0, ST(stream)>>>(prefix, ctx, suffix, pos, x, C, Te, n_ctx, Tfull, D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_prompt_splice_fwd(float* x, const float* prompt, int N, int T, int row0, int n_ctx, int D,
+                                     void* stream) {
+  if (!x || !prompt || row0 < 0 || row0 + n_ctx > T || D % 4) return MFK_EARG;
+  splice_fwd_kernel<<<N * n_ctx, 128, 0, ST(stream)>>>(x, prompt, T, row0, n_ctx, D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int N, int T, int row0, int n_ctx, int D,
+                                     int round_fp16, int zero_rows, void* stream) {
+  if (!g || !dprompt || row0 < 0 || row0 + n_ctx > T) return MFK_EARG;
+  dim3 grid((D + 127) / 128, n_ctx);
+  splice_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(g, static_cast<bf16*>(g_bf16), dprompt, N, T, row0, n_ctx, D,
+                                                  round_fp16, zero_rows);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16, int R, int D,
+                                void* stream) {
+  if (!dx || !rowidx || !g || R <= 0) return MFK_EARG;
+  scatter_rows_kernel<<<R, 128, 0, ST(stream)>>>(dx, rowidx, g, static_cast<bf16*>(g_bf16), D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_transpose_bf16(const void* in, int in_is_f32, long long ldi, void* out, long long ldo, void* copy,
+                                  long long ldc, int M, int N, void* stream) {
+  if (!in || !out || M <= 0 || N <= 0) return MFK_EARG;
+  dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+  if (in_is_f32)
+    transpose_to_bf16_kernel<float><<<grid, block, 0, ST(stream)>>>(static_cast<const float*>(in), ldi, static_cast<bf16*>(out), ldo, static_cast<bf16*>(copy), ldc, M, N);
+  else
+    transpose_to_bf16_kernel<bf16><<<grid, block, 0, ST(stream)>>>(static_cast<const bf16*>(in), ldi, static_cast<bf16*>(out), ldo, static_cast<bf16*>(copy), ldc, M, N);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  if (!in || !out || n <= 0) return MFK_EARG;
+  const long long thr = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, ST(stream)>>>(in, static_cast<bf16*>(out), n);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_linear_small_fwd(const float* x, const float* W, const float* b, float* y, int m, int N, int K,
+                                    void* stream) {
+  if (!x || !W || !y || m <= 0) return MFK_EARG;
+  linear_small_fwd_kernel<<<(N + 7) / 8, 256, 0, ST(stream)>>>(x, W, b, y, m, N, K);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_linear_small_bwd(const float* x, const float* W, const float* dy, float* dW, float* db,
+                                    const float* dx_add, float* dx, int m, int N, int K, void* stream) {
+  if (!x || !W || !dy || m <= 0) return MFK_EARG;
+  if (dW) linear_small_bwd_w_kernel<<<N, 128, 0, ST(stream)>>>(x, dy, dW, db, m, N, K);
+  if (dx) linear_small_bwd_x_kernel<<<(K + 127) / 128, 128, 0, ST(stream)>>>(W, dy, dx_add, dx, m, N, K);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}

@@ -1,0 +1,210 @@
+// FedAvg reduction, validity scan and the fused clip + SGD step (HBM-bound).
+//
+// mfk_fedavg_reduce restates MaPLeFederated.safe_average_weights (trainers/maple_fed.py:309-315):
+//   per element: fp32 cast -> nan_to_num(nan=0, posinf=1e4, neginf=-1e4) -> sum over clients in the
+//   FIXED order of torch's CPU cascade sum (sequential inside chunks of 16 clients, chunk sums added
+//   sequentially, remainder last) -> true division by K -> fp32 result + fp16-rounded result (`.half()`).
+// Weighted mode (north_star extension): each row is multiplied by float(n_k) first and the divisor is
+// float(sum n_k). The order does not depend on the number of GPUs, so every rank that holds the gathered
+// client tensors computes bit-identical results. A NaN/Inf flag word per client replaces
+// check_weights_valid (trainers/maple_fed.py:317-325).
+#include "mfk_common.cuh"
+#include "../../include/mfk.h"
+
+namespace {
+using namespace mfk;
+
+__device__ __forceinline__ float sanitize(float v, int* flag, bool& bad_nan, bool& bad_inf) {
+  if (isnan(v)) { bad_nan = true; return 0.f; }
+  if (isinf(v)) { bad_inf = true; return v > 0.f ? 1e4f : -1e4f; }
+  return v;
+}
+
+template <typename TIN>
+__device__ __forceinline__ float4 load4(const TIN* p, long long i);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p, long long i) {
+  return *reinterpret_cast<const float4*>(p + i);
+}
+template <>
+__device__ __forceinline__ float4 load4<__half>(const __half* p, long long i) {
+  uint2 u = *reinterpret_cast<const uint2*>(p + i);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x)), b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+fedavg_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ weights, int K, long long n,
+              float divisor, float* __restrict__ out32, __half* __restrict__ out16, int* __restrict__ flags) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 chunk = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int full = K / 16;
+    for (int k = 0; k < K; ++k) {
+      const TIN* p = static_cast<const TIN*>(ptrs[k]);
+      float4 v;
+      if (i + 3 < n) {
+        v = load4<TIN>(p, i);
+      } else {
+        v.x = (float)p[i];
+        v.y = i + 1 < n ? (float)p[i + 1] : 0.f;
+        v.z = i + 2 < n ? (float)p[i + 2] : 0.f;
+        v.w = 0.f;
+      }
+      bool bn = false, bi = false;
+      v.x = sanitize(v.x, flags, bn, bi); v.y = sanitize(v.y, flags, bn, bi);
+      v.z = sanitize(v.z, flags, bn, bi); v.w = sanitize(v.w, flags, bn, bi);
+      if (flags && (bn || bi)) atomicOr(&flags[k], (bn ? 1 : 0) | (bi ? 2 : 0));
+      if (weights) {
+        const float w = weights[k];
+        v.x = __fmul_rn(v.x, w); v.y = __fmul_rn(v.y, w); v.z = __fmul_rn(v.z, w); v.w = __fmul_rn(v.w, w);
+      }
+      // explicit __fadd_rn: no FMA contraction, order is the contract
+      const int pos = k & 15;
+      if (pos == 0) chunk = v;
+      else { chunk.x = __fadd_rn(chunk.x, v.x); chunk.y = __fadd_rn(chunk.y, v.y); chunk.z = __fadd_rn(chunk.z, v.z); chunk.w = __fadd_rn(chunk.w, v.w); }
+      const bool chunk_done = (pos == 15) || (k == K - 1);
+      if (chunk_done) {
+        const int ci = k / 16;
+        if (ci == 0) total = chunk;
+        else { total.x = __fadd_rn(total.x, chunk.x); total.y = __fadd_rn(total.y, chunk.y); total.z = __fadd_rn(total.z, chunk.z); total.w = __fadd_rn(total.w, chunk.w); }
+      }
+    }
+    (void)full;
+    float4 m;
+    m.x = __fdiv_rn(total.x, divisor); m.y = __fdiv_rn(total.y, divisor);
+    m.z = __fdiv_rn(total.z, divisor); m.w = __fdiv_rn(total.w, divisor);
+    if (i + 3 < n) {
+      if (out32) *reinterpret_cast<float4*>(out32 + i) = m;
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
+        *reinterpret_cast<uint2*>(out16 + i) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    } else {
+      const float mm[4] = {m.x, m.y, m.z, m.w};
+      for (int e = 0; e < 4 && i + e < n; ++e) {
+        if (out32) out32[i + e] = mm[e];
+        if (out16) out16[i + e] = __float2half_rn(mm[e]);
+      }
+    }
+  }
+}
+
+template <typename TIN>
+__global__ void check_finite_kernel(const TIN* __restrict__ p, long long n, int* __restrict__ flag) {
+  bool bn = false, bi = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = (float)p[i];
+    bn |= isnan(v);
+    bi |= isinf(v);
+  }
+  if (bn || bi) atomicOr(flag, (bn ? 1 : 0) | (bi ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------- clip_grad_norm_ + SGD
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += g[i] * g[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ partial, int P, float* __restrict__ norm_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t = 0.f;
+    for (int p = 0; p < P; ++p) t += partial[p];
+    norm_out[0] = sqrtf(t);
+  }
+}
+// torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.SGD.step (trainers/maple.py:592-598).
+// hp = {lr, momentum, dampening, weight_decay, max_norm, nesterov, first_step}
+__global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom, long long n,
+                                const float* __restrict__ hp, const float* __restrict__ total_norm) {
+  const float lr = hp[0], mu = hp[1], damp = hp[2], wd = hp[3], max_norm = hp[4];
+  const bool nesterov = hp[5] != 0.f, first = hp[6] != 0.f;
+  float coef = 1.f;
+  if (max_norm > 0.f) coef = fminf(max_norm / (total_norm[0] + 1e-6f), 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gc = g[i] * coef;
+    g[i] = gc;  // grads are clipped in place, as clip_grad_norm_ does
+    float d = gc + wd * p[i];
+    if (mu != 0.f) {
+      const float b = first ? d : mu * mom[i] + (1.f - damp) * d;
+      mom[i] = b;
+      d = nesterov ? d + mu * b : b;
+    }
+    p[i] -= lr * d;
+  }
+}
+
+}  // namespace
+
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int mfk_fedavg_reduce(const void* const* client_ptrs_dev, const float* weights_dev, float divisor, int K,
+                                 long long n, int in_is_fp16, float* out_f32, void* out_f16, int* flags_dev,
+                                 void* stream) {
+  if (!client_ptrs_dev || K <= 0 || n <= 0 || (!out_f32 && !out_f16) || !(divisor > 0.f)) return MFK_EARG;
+  long long thr = (n + 3) / 4;
+  long long blocks = (thr + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (in_is_fp16)
+    fedavg_kernel<__half><<<(unsigned)blocks, 256, 0, ST(stream)>>>(client_ptrs_dev, weights_dev, K, n, divisor, out_f32, static_cast<__half*>(out_f16), flags_dev);
+  else
+    fedavg_kernel<float><<<(unsigned)blocks, 256, 0, ST(stream)>>>(client_ptrs_dev, weights_dev, K, n, divisor, out_f32, static_cast<__half*>(out_f16), flags_dev);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_check_finite(const void* p, long long n, int dtype, int* flag_dev, void* stream) {
+  if (!p || n <= 0 || !flag_dev) return MFK_EARG;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dtype == 0) check_finite_kernel<float><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const float*>(p), n, flag_dev);
+  else if (dtype == 1) check_finite_kernel<__half><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const __half*>(p), n, flag_dev);
+  else if (dtype == 2) check_finite_kernel<bf16><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(p), n, flag_dev);
+  else return MFK_EARG;
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_grad_norm(const float* g, long long n, float* partial_ws, float* norm_out, void* stream) {
+  if (!g || n <= 0 || !partial_ws || !norm_out) return MFK_EARG;
+  const int P = 296;
+  sumsq_partial_kernel<<<P, 256, 0, ST(stream)>>>(g, n, partial_ws);
+  sumsq_final_kernel<<<1, 32, 0, ST(stream)>>>(partial_ws, P, norm_out);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_sgd_step(float* p, float* g, float* mom, long long n, const float* hyper_dev,
+                            const float* total_norm_dev, void* stream) {
+  if (!p || !g || !mom || n <= 0 || !hyper_dev || !total_norm_dev) return MFK_EARG;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sgd_step_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(p, g, mom, n, hyper_dev, total_norm_dev);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_version(void) { return 100; }
+
+extern "C" const char* mfk_error_string(int code) {
+  switch (code) {
+    case MFK_OK: return "ok";
+    case MFK_EARG: return "mfk: invalid argument";
+    case MFK_ESHAPE: return "mfk: unsupported shape";
+    case MFK_EALIGN: return "mfk: pointer or leading dimension not 16-byte aligned";
+    case MFK_EDRIVER: return "mfk: CUDA driver entry point unavailable / tensor-map encode failed";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "mfk: unknown error";
+  }
+}

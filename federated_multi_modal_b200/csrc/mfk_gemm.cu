@@ -1,0 +1,369 @@
+// tcgen05 / TMEM / TMA GEMM with fused epilogues for the MaPLe towers (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )       A, B bf16 row-major (K contiguous), fp32 accumulate
+//
+// One kernel covers the reference's call sites (SURVEY.md §2.2 K1,K4,K6,K7,K8,K12,K13 and their
+// dgrad / wgrad forms, K15): nn.MultiheadAttention in_proj / out_proj (clip/model.py:274,303-305,350),
+// mlp.c_fc + QuickGELU and mlp.c_proj (clip/model.py:276-280,351), conv1-as-GEMM (clip/model.py:514),
+// `@ proj` / `@ text_projection` (clip/model.py:569-570, trainers/maple.py:76).
+//
+// Design: persistent, warp-specialised. warp0 = TMA producer (one thread), warp1 = tcgen05.mma issuer
+// (one thread), warp2 = TMEM allocator, warps4-7 = epilogue (one TMEM lane == one output row per thread).
+// smem ring of kStages x {A 128x64, B BNx64} bf16 tiles in 128-byte swizzle, filled by TMA and consumed
+// straight by UMMA descriptors; two 256-column TMEM accumulators so the epilogue of tile i overlaps the
+// MMAs of tile i+1. The last partial wave of tiles is split into narrower tiles (runtime UMMA N) so the
+// tail spreads over all SMs (50 M-tiles x a few N-tiles quantises badly on 148 SMs otherwise).
+#include "mfk_common.cuh"
+#include "../../include/mfk.h"
+
+namespace {
+
+using namespace mfk;
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
+constexpr int UK = 16;        // UMMA K for 16-bit inputs
+constexpr int BOXN = 64;      // B rows per TMA box (tiles are 64/128/256 wide)
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct GemmParams {
+  int M, N, K;
+  int n_big;        // number of full-width N tiles
+  int bn;           // full tile width (128 or 256)
+  int full_tiles;   // tiles [0, full_tiles) are full width
+  int split;        // each remaining big tile is split into `split` tiles of width bn/split
+  int total_tiles;
+  const float* bias;
+  int act;          // 0 none, 1 QuickGELU, 2 multiply by QuickGELU'(aux)
+  const bf16* aux;
+  long long ldaux;
+  const float* res;
+  long long ldres;
+  float* out32;
+  long long ld32;
+  bf16* out16;
+  long long ld16;
+  bf16* outpre;
+  long long ldpre;
+};
+
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0, int& n0, int& w) {
+  int big, sub = 0;
+  if (t < p.full_tiles) {
+    big = t;
+    w = p.bn;
+  } else {
+    int r = t - p.full_tiles;
+    big = p.full_tiles + r / p.split;
+    sub = r % p.split;
+    w = p.bn / p.split;
+  }
+  m0 = (big / p.n_big) * BM;
+  n0 = (big % p.n_big) * p.bn + sub * w;
+}
+
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  constexpr uint32_t kABytes = BM * BK * 2;
+  constexpr uint32_t kBBytes = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int m0, n0, w;
+        decode_tile(p, t, m0, n0, w);
+        const uint32_t tx = kABytes + (uint32_t)w * BK * 2;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          for (int j = 0; j < w; j += BOXN)
+            tma_load_2d(&tmB, &full_bar[stage], sb + j * (BK * 2), kb * BK, n0 + j);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        int m0, n0, w;
+        decode_tile(p, t, m0, n0, w);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(BM, w, 0, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance 16 elements (32 B) inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int m0, n0, w;
+      decode_tile(p, t, m0, n0, w);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      for (int c = 0; c < w; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tc_wait_ld();
+        const int col = n0 + c;
+        if (row_ok && col < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b = __ldg(b4 + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.act == 1) {
+            if (p.outpre) {
+              uint4* o = reinterpret_cast<uint4*>(p.outpre + (size_t)row * p.ldpre + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                  pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            }
+            // the activation is applied to the bf16-rounded pre-activation that backward will re-read
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quickgelu(__bfloat162float(__float2bfloat16_rn(v[j])));
+          } else if (p.act == 2) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 a = __ldg(a4 + j);
+              float2 u0 = unpack_bf16(a.x), u1 = unpack_bf16(a.y), u2 = unpack_bf16(a.z), u3 = unpack_bf16(a.w);
+              v[8 * j] *= dquickgelu(u0.x); v[8 * j + 1] *= dquickgelu(u0.y);
+              v[8 * j + 2] *= dquickgelu(u1.x); v[8 * j + 3] *= dquickgelu(u1.y);
+              v[8 * j + 4] *= dquickgelu(u2.x); v[8 * j + 5] *= dquickgelu(u2.y);
+              v[8 * j + 6] *= dquickgelu(u3.x); v[8 * j + 7] *= dquickgelu(u3.y);
+            }
+          }
+          if (p.res) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)row * p.ldres + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 x = r4[j];
+              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            }
+          }
+          if (p.out32) {
+            float4* o = reinterpret_cast<float4*>(p.out32 + (size_t)row * p.ld32 + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.out16) {
+            uint4* o = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int kStages>
+constexpr size_t gemm_smem_bytes() {
+  return (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + (2 * kStages + 4) * 8 + 16 + 1024;
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return MFK_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return MFK_EDRIVER;
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return MFK_OK;
+}
+
+int mfk_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                          uint32_t box_rows, uint32_t box_cols) {
+  int rc = load_encode();
+  if (rc != MFK_OK) return rc;
+  if (!mfk_aligned16(base) || (ld_elems * 2) % 16 != 0) return MFK_EALIGN;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MFK_OK : MFK_EDRIVER;
+}
+
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int kStages>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                       cudaStream_t st) {
+  static bool configured = false;
+  constexpr size_t smem = gemm_smem_bytes<BN, kStages>();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  gemm_bf16_tn_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                             const float* bias, int act, const void* aux, long long ldaux, const float* residual,
+                             long long ldres, float* out_f32, long long ld32, void* out_bf16, long long ld16,
+                             void* out_pre_bf16, long long ldpre, int tile_n, void* stream) {
+  if (!A || !B || M <= 0 || N <= 0 || K <= 0) return MFK_EARG;
+  if (N % 32 != 0 || lda % 8 != 0 || ldb % 8 != 0 || lda < K || ldb < K) return MFK_ESHAPE;
+  if (act < 0 || act > 2 || (act == 2 && !aux)) return MFK_EARG;
+  if (!out_f32 && !out_bf16) return MFK_EARG;
+  if ((out_f32 && (ld32 % 4 || !mfk_aligned16(out_f32))) || (out_bf16 && (ld16 % 8 || !mfk_aligned16(out_bf16))) ||
+      (out_pre_bf16 && (ldpre % 8 || !mfk_aligned16(out_pre_bf16))) || (aux && (ldaux % 8 || !mfk_aligned16(aux))) ||
+      (residual && (ldres % 4 || !mfk_aligned16(residual))) || (bias && !mfk_aligned16(bias)))
+    return MFK_EALIGN;
+
+  const int sms = num_sms();
+  const int m_tiles = (M + BM - 1) / BM;
+  // full tile width: 256 unless N is small or the caller forces 128
+  int bn = (tile_n == 128 || tile_n == 256) ? tile_n : 256;
+  if (tile_n == 0 && N < 256) bn = 128;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bn = bn;
+  p.n_big = (N + bn - 1) / bn;
+  const int big = m_tiles * p.n_big;
+  p.full_tiles = (big / sms) * sms;
+  const int rem = big - p.full_tiles;
+  p.split = 1;
+  if (rem > 0) {
+    const int max_split = bn / 64;
+    while (p.split * 2 <= max_split && rem * p.split * 2 <= sms) p.split *= 2;
+  }
+  p.total_tiles = p.full_tiles + rem * p.split;
+  p.bias = bias; p.act = act;
+  p.aux = static_cast<const bf16*>(aux); p.ldaux = ldaux;
+  p.res = residual; p.ldres = ldres;
+  p.out32 = out_f32; p.ld32 = ld32;
+  p.out16 = static_cast<bf16*>(out_bf16); p.ld16 = ld16;
+  p.outpre = static_cast<bf16*>(out_pre_bf16); p.ldpre = ldpre;
+
+  CUtensorMap tmA, tmB;
+  int rc = mfk_make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+  if (rc != MFK_OK) return rc;
+  rc = mfk_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BOXN, BK);
+  if (rc != MFK_OK) return rc;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, p, grid, st);
+  return launch_gemm<128, 6>(tmA, tmB, p, grid, st);
+}

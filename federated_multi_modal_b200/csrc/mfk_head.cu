@@ -1,0 +1,188 @@
+// Fused logits / loss head and its gradient (trainers/maple.py:325-372):
+//   s = min(exp(logit_scale), 100); a = F.normalize(img, eps 1e-8); t = F.normalize(txt, eps 1e-8)
+//   logits = s * a t^T;  loss = CE(logits, y) + 0.5 * (1 - mean_b cos(a_b, t_{y_b}))
+// All fp32; every reduction has a fixed order (bit-reproducible run to run).
+#include "mfk_common.cuh"
+#include "../../include/mfk.h"
+
+namespace {
+using namespace mfk;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  return s;
+}
+
+// rows [0,B) = image features, rows [B,B+C) = text features
+__global__ void head_normalize_kernel(const float* __restrict__ fi, const float* __restrict__ ft, float* __restrict__ a,
+                                      float* __restrict__ t, float* __restrict__ ni, float* __restrict__ nt, int B,
+                                      int C, int E) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const float* src = r < B ? fi + (size_t)r * E : ft + (size_t)(r - B) * E;
+  float* dst = r < B ? a + (size_t)r * E : t + (size_t)(r - B) * E;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) q += src[i] * src[i];
+  const float nrm = fmaxf(sqrtf(block_sum(q, red)), 1e-8f);
+  for (int i = threadIdx.x; i < E; i += blockDim.x) dst[i] = src[i] / nrm;
+  if (threadIdx.x == 0) (r < B ? ni[r] : nt[r - B]) = nrm;
+}
+
+__global__ void head_logits_kernel(const float* __restrict__ a, const float* __restrict__ t,
+                                   const float* __restrict__ logit_scale, float* __restrict__ logits, int B, int C,
+                                   int E) {
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)B * C) return;
+  const int b = (int)(w / C), c = (int)(w % C);
+  float s = 0.f;
+  for (int i = lane; i < E; i += 32) s += a[(size_t)b * E + i] * t[(size_t)c * E + i];
+  s = warp_sum(s);
+  if (lane == 0) logits[(size_t)b * C + c] = fminf(expf(logit_scale[0]), 100.f) * s;
+}
+
+// per image: CE term, dlogits, cosine alignment term
+__global__ void head_rows_kernel(const float* __restrict__ logits, const long long* __restrict__ label,
+                                 const float* __restrict__ a, const float* __restrict__ t, float* __restrict__ dlog,
+                                 float* __restrict__ loss_b, float* __restrict__ cos_o, float* __restrict__ na2_o,
+                                 float* __restrict__ nt2_o, int B, int C, int E) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const int y = (int)label[b];
+  const float* lg = logits + (size_t)b * C;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lg[c]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  float se = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(lg[c] - mx);
+  se = block_sum(se, red);
+  const float lse = mx + logf(se);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    dlog[(size_t)b * C + c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) / (float)B;
+  float dot = 0.f, qa = 0.f, qt = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float av = a[(size_t)b * E + i], tv = t[(size_t)y * E + i];
+    dot += av * tv; qa += av * av; qt += tv * tv;
+  }
+  dot = block_sum(dot, red);
+  qa = block_sum(qa, red);
+  qt = block_sum(qt, red);
+  if (threadIdx.x == 0) {
+    const float na2 = fmaxf(sqrtf(qa), 1e-8f), nt2 = fmaxf(sqrtf(qt), 1e-8f);
+    const float cs = dot / (na2 * nt2);
+    cos_o[b] = cs; na2_o[b] = na2; nt2_o[b] = nt2;
+    loss_b[b] = (lse - lg[y]) / (float)B + 0.5f * (1.f - cs) / (float)B;
+  }
+}
+
+__global__ void head_loss_kernel(const float* __restrict__ loss_b, float* __restrict__ loss, int B) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float ce = 0.f;
+    for (int b = 0; b < B; ++b) ce += loss_b[b];
+    loss[0] = ce;
+  }
+}
+
+// d image_features[b,:]
+__global__ void head_grad_img_kernel(const float* __restrict__ dlog, const long long* __restrict__ label,
+                                     const float* __restrict__ a, const float* __restrict__ t,
+                                     const float* __restrict__ ni, const float* __restrict__ cos_i,
+                                     const float* __restrict__ na2_i, const float* __restrict__ nt2_i,
+                                     const float* __restrict__ logit_scale, float* __restrict__ dfi, int B, int C,
+                                     int E) {
+  __shared__ float red[8];
+  extern __shared__ float da[];
+  const int b = blockIdx.x;
+  const int y = (int)label[b];
+  const float s = fminf(expf(logit_scale[0]), 100.f);
+  const float dcos = -0.5f / (float)B, cs = cos_i[b], na2 = na2_i[b], nt2 = nt2_i[b];
+  float proj = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc += dlog[(size_t)b * C + c] * t[(size_t)c * E + i];
+    const float av = a[(size_t)b * E + i];
+    acc = s * acc + dcos * (t[(size_t)y * E + i] / (na2 * nt2) - cs * av / (na2 * na2));
+    da[i] = acc;
+    proj += av * acc;
+  }
+  proj = block_sum(proj, red);
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    dfi[(size_t)b * E + i] = (da[i] - a[(size_t)b * E + i] * proj) / ni[b];
+}
+
+// d text_features[c,:]
+__global__ void head_grad_txt_kernel(const float* __restrict__ dlog, const long long* __restrict__ label,
+                                     const float* __restrict__ a, const float* __restrict__ t,
+                                     const float* __restrict__ nt, const float* __restrict__ cos_i,
+                                     const float* __restrict__ na2_i, const float* __restrict__ nt2_i,
+                                     const float* __restrict__ logit_scale, float* __restrict__ dft, int B, int C,
+                                     int E) {
+  __shared__ float red[8];
+  extern __shared__ float dt[];
+  const int c = blockIdx.x;
+  const float s = fminf(expf(logit_scale[0]), 100.f);
+  const float dcos = -0.5f / (float)B;
+  float proj = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float tv = t[(size_t)c * E + i];
+    float acc = 0.f, al = 0.f;
+    for (int b = 0; b < B; ++b) acc += dlog[(size_t)b * C + c] * a[(size_t)b * E + i];
+    for (int b = 0; b < B; ++b)
+      if ((int)label[b] == c)
+        al += dcos * (a[(size_t)b * E + i] / (na2_i[b] * nt2_i[b]) - cos_i[b] * tv / (nt2_i[b] * nt2_i[b]));
+    acc = s * acc + al;
+    dt[i] = acc;
+    proj += tv * acc;
+  }
+  proj = block_sum(proj, red);
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    dft[(size_t)c * E + i] = (dt[i] - t[(size_t)c * E + i] * proj) / nt[c];
+}
+
+}  // namespace
+
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" long long mfk_head_workspace_floats(int B, int C, int E) {
+  return (long long)(B + C) * E + (B + C) + (long long)B * C + 4LL * B + 8;
+}
+
+// workspace layout (floats): a[B,E] t[C,E] ni[B] nt[C] dlog[B,C] loss_b[B] cos[B] na2[B] nt2[B]
+extern "C" int mfk_head_forward_backward(const float* img_feat, const float* txt_feat, const float* logit_scale,
+                                         const long long* label, float* logits, float* loss, float* d_img,
+                                         float* d_txt, float* ws, int B, int C, int E, void* stream) {
+  if (!img_feat || !txt_feat || !logit_scale || !logits || !ws || B <= 0 || C <= 0 || E <= 0) return MFK_EARG;
+  const bool train = label != nullptr;
+  if (train && (!loss || !d_img || !d_txt)) return MFK_EARG;
+  float* a = ws;
+  float* t = a + (size_t)B * E;
+  float* ni = t + (size_t)C * E;
+  float* nt = ni + B;
+  float* dlog = nt + C;
+  float* loss_b = dlog + (size_t)B * C;
+  float* cosb = loss_b + B;
+  float* na2 = cosb + B;
+  float* nt2 = na2 + B;
+  head_normalize_kernel<<<B + C, 128, 0, ST(stream)>>>(img_feat, txt_feat, a, t, ni, nt, B, C, E);
+  const long long warps = (long long)B * C;
+  head_logits_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ST(stream)>>>(a, t, logit_scale, logits, B, C, E);
+  if (train) {
+    head_rows_kernel<<<B, 128, 0, ST(stream)>>>(logits, label, a, t, dlog, loss_b, cosb, na2, nt2, B, C, E);
+    head_loss_kernel<<<1, 32, 0, ST(stream)>>>(loss_b, loss, B);
+    head_grad_img_kernel<<<B, 128, E * sizeof(float), ST(stream)>>>(dlog, label, a, t, ni, cosb, na2, nt2, logit_scale, d_img, B, C, E);
+    head_grad_txt_kernel<<<C, 128, E * sizeof(float), ST(stream)>>>(dlog, label, a, t, nt, cosb, na2, nt2, logit_scale, d_txt, B, C, E);
+  }
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}

@@ -1,0 +1,145 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point of include/mfk.h).
+
+All tensors must live on the current CUDA device; work is enqueued on torch's current stream.
+No op here has a CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, stream_ptr
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: libmfk kernels need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.dim() >= 2 and t.stride(-1) != 1:
+        raise ValueError(f"{name}: innermost dimension must be contiguous")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = 0,
+         aux: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
+         out_pre: Optional[torch.Tensor] = None, k: Optional[int] = None, tile_n: int = 0):
+    """out[M,N] = epi(a[M,K] @ b[N,K]^T); see mfk_gemm_bf16. `k` overrides K (padded operands)."""
+    _chk(a, BF16, "a"); _chk(b, BF16, "b")
+    M, N = a.shape[0], b.shape[0]
+    K = a.shape[1] if k is None else k
+    ld = lambda t: t.stride(0) if t is not None else 0
+    call("mfk_gemm_bf16", a, a.stride(0), b, b.stride(0), M, N, K, bias, act, aux, ld(aux), residual, ld(residual),
+         out_f32, ld(out_f32), out_bf16, ld(out_bf16), out_pre, ld(out_pre), tile_n, stream_ptr())
+
+
+def attn_fwd(qkv, out, lse, N, T, heads, causal):
+    _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out")
+    call("mfk_attn_fwd", qkv, out, lse, N, T, heads, int(causal), stream_ptr())
+
+
+def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal):
+    call("mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, int(causal), stream_ptr())
+
+
+def layernorm_fwd(x, gamma, beta, *, rowidx=None, y_bf16=None, y_f32=None, x_save=None, mean=None, rstd=None,
+                  M=None, eps=1e-5):
+    _chk(x, F32, "x")
+    D = x.shape[-1]
+    M = (rowidx.numel() if rowidx is not None else x.numel() // D) if M is None else M
+    call("mfk_layernorm_fwd", x, rowidx, gamma, beta, y_bf16, y_f32, x_save, mean, rstd, M, D, eps, stream_ptr())
+
+
+def ln_bwd_ctas(M: int) -> int:
+    return call("mfk_ln_bwd_ctas", M)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, g_in=None, g_out, g_out_bf16=None, dgamma=None, dbeta=None,
+                  partial_ws=None, accumulate=False, M=None):
+    D = x.shape[-1]
+    M = x.numel() // D if M is None else M
+    call("mfk_layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma,
+         dbeta, partial_ws, int(accumulate), M, D, stream_ptr())
+
+
+def colsum(x, out, partial_ws, accumulate=False):
+    call("mfk_colsum", x, int(x.dtype == BF16), x.stride(0), x.shape[0], x.shape[1], out, partial_ws,
+         int(accumulate), stream_ptr())
+
+
+def patch_im2col(img, out):
+    _chk(img, F32, "img")
+    call("mfk_patch_im2col", img, out, img.shape[0], img.shape[-1], stream_ptr())
+
+
+def vis_assemble_lnpre(tok, cls, pos, shared_ctx, gamma, beta, x0_save, x, mean, rstd, B, T, n_ctx, eps=1e-5):
+    call("mfk_vis_assemble_lnpre", tok, cls, pos, shared_ctx, gamma, beta, x0_save, x, mean, rstd, B, T, n_ctx,
+         x.shape[-1], eps, stream_ptr())
+
+
+def text_assemble(prefix, ctx, suffix, pos, x, C, Te, n_ctx, Tfull):
+    call("mfk_text_assemble", prefix, ctx, suffix, pos, x, C, Te, n_ctx, Tfull, x.shape[-1], stream_ptr())
+
+
+def prompt_splice_fwd(x, prompt, N, T, row0, n_ctx):
+    call("mfk_prompt_splice_fwd", x, prompt, N, T, row0, n_ctx, x.shape[-1], stream_ptr())
+
+
+def prompt_splice_bwd(g, g_bf16, dprompt, N, T, row0, n_ctx, round_fp16=True, zero_rows=True):
+    call("mfk_prompt_splice_bwd", g, g_bf16, dprompt, N, T, row0, n_ctx, g.shape[-1], int(round_fp16),
+         int(zero_rows), stream_ptr())
+
+
+def scatter_rows(dx, rowidx, g, g_bf16):
+    call("mfk_scatter_rows", dx, rowidx, g, g_bf16, dx.shape[0], dx.shape[1], stream_ptr())
+
+
+def transpose_bf16(inp, out, copy=None):
+    """out[N, ldo] = inp[M, N]^T as bf16 (inp fp32 or bf16)."""
+    call("mfk_transpose_bf16", inp, int(inp.dtype == F32), inp.stride(0), out, out.stride(0), copy,
+         copy.stride(0) if copy is not None else 0, inp.shape[0], inp.shape[1], stream_ptr())
+
+
+def cast_bf16(inp, out):
+    call("mfk_cast_f32_bf16", inp, out, inp.numel(), stream_ptr())
+
+
+def linear_small_fwd(x, W, b, y):
+    call("mfk_linear_small_fwd", x, W, b, y, x.shape[0], W.shape[0], W.shape[1], stream_ptr())
+
+
+def linear_small_bwd(x, W, dy, *, dW=None, db=None, dx_add=None, dx=None):
+    call("mfk_linear_small_bwd", x, W, dy, dW, db, dx_add, dx, x.shape[0], W.shape[0], W.shape[1], stream_ptr())
+
+
+def head_workspace_floats(B, C, E) -> int:
+    return call("mfk_head_workspace_floats", B, C, E)
+
+
+def head_forward_backward(img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws):
+    B, E = img_feat.shape
+    C = txt_feat.shape[0]
+    call("mfk_head_forward_backward", img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws, B, C, E,
+         stream_ptr())
+
+
+def fedavg_reduce(ptrs_dev, weights_dev, divisor, K, n, in_is_fp16, out_f32, out_f16, flags_dev):
+    call("mfk_fedavg_reduce", ptrs_dev, weights_dev, float(divisor), K, n, int(in_is_fp16), out_f32, out_f16,
+         flags_dev, stream_ptr())
+
+
+def check_finite(t, flag_dev):
+    code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[t.dtype]
+    call("mfk_check_finite", t, t.numel(), code, flag_dev, stream_ptr())
+
+
+def grad_norm(g, partial_ws, norm_out):
+    call("mfk_grad_norm", g, g.numel(), partial_ws, norm_out, stream_ptr())
+
+
+def sgd_step(p, g, mom, hyper_dev, total_norm_dev, n=None):
+    call("mfk_sgd_step", p, g, mom, p.numel() if n is None else n, hyper_dev, total_norm_dev, stream_ptr())

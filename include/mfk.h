@@ -1,0 +1,131 @@
+/* mfk.h — C ABI of libmfk (MaPLe-Federated Kernels for NVIDIA B200, sm_100a).
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * tahaspc82442/federated_multi_modal: the MaPLe CustomCLIP forward/backward step and the
+ * per-round FedAvg. The reference has NO native code or FFI of its own (pure PyTorch); each
+ * entry point below replaces the torch call sites cited next to it (paths relative to the
+ * reference tree). INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions:
+ *  - plain pointers and sizes, no torch types; all pointers are DEVICE pointers unless noted;
+ *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) of the caller's current
+ *    device and returns immediately; no internal threads, no allocation (caller passes outputs and
+ *    workspaces), no exceptions: return 0 = ok, <0 = argument/shape/alignment error, >0 = cudaError_t;
+ *  - matrices are row-major token-major [rows, D]; `ld*` are leading dimensions in ELEMENTS;
+ *    bf16 matrices need 16-byte aligned base pointers and ld % 8 == 0;
+ *  - "bf16" is __nv_bfloat16, "f16" is __half; activations/weights of the towers are bf16, the
+ *    residual stream, LayerNorm statistics, gradients of parameters and the loss head are fp32.
+ */
+#ifndef MFK_H_
+#define MFK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int mfk_version(void);
+const char* mfk_error_string(int code);
+
+/* ------------------------------------------------------------------ tensor-core GEMM (tcgen05/TMEM/TMA)
+ * out[M,N] = epi( A[M,K] * B[N,K]^T ), A and B bf16 with K contiguous, fp32 accumulation.
+ *   epi: (+bias[N] fp32) -> act -> (+residual[M,N] fp32) -> out_f32 and/or out_bf16
+ *   act 0: none | 1: QuickGELU x*sigmoid(1.702x), pre-activation optionally stored (out_pre_bf16)
+ *       2: multiply by QuickGELU'(aux[M,N] bf16)   (backward of act 1)
+ * N % 32 == 0. tile_n: 0 = auto, 128 or 256 = forced full-tile width.
+ * Replaces: nn.MultiheadAttention in_proj/out_proj (clip/model.py:274,303-305,350), mlp.c_fc +
+ * QuickGELU + c_proj (clip/model.py:276-280,162-164,351), conv1 as GEMM (clip/model.py:484,514),
+ * `x @ self.proj` (clip/model.py:569-570), `@ self.text_projection` (trainers/maple.py:76), and
+ * autograd's dgrad/wgrad of the same (trainers/maple.py:590).                                        */
+int mfk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                  const float* bias, int act, const void* aux, long long ldaux, const float* residual,
+                  long long ldres, float* out_f32, long long ld32, void* out_bf16, long long ld16,
+                  void* out_pre_bf16, long long ldpre, int tile_n, void* stream);
+
+/* ------------------------------------------------------------------ attention (head dim 64, T <= 256)
+ * qkv[N*T, 3*heads*64] bf16 (q|k|v, head h = columns h*64..h*64+63 of each part) -> out[N*T, heads*64].
+ * softmax(q k^T / 8 [+ causal mask]) v per (sequence, head). lse[N,heads,T] (log2 domain) is saved for
+ * backward (may be NULL for inference). Replaces nn.MultiheadAttention's core inside
+ * ResidualAttentionBlock_MaPLe.attention (clip/model.py:303-305) with the additive causal mask of
+ * CLIP.build_attention_mask (clip/model.py:679-685) when causal != 0.                                 */
+int mfk_attn_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int causal, void* stream);
+/* dqkv[N*T, 3*heads*64] bf16 from d_out; delta_ws: N*heads*T floats of scratch. */
+int mfk_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
+                 void* dqkv, int N, int T, int heads, int causal, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm (clip/model.py:153-159)
+ * fp32 statistics, eps as given (1e-5), D in {128, 512, 768}. rowidx (int32[M], may be NULL) gathers
+ * source rows first — used for ln_post on CLS rows (clip/model.py:567) and ln_final on EOT rows
+ * (trainers/maple.py:72-76; LN is row-wise so gather-then-LN == LN-then-gather).
+ * Outputs (each optional): y_bf16, y_f32, x_save (gathered fp32 input), mean[M], rstd[M].           */
+int mfk_layernorm_fwd(const float* x, const int* rowidx, const float* gamma, const float* beta, void* y_bf16,
+                      float* y_f32, float* x_save, float* mean, float* rstd, int M, int D, float eps,
+                      void* stream);
+/* g_out = (g_in ? g_in : 0) + dLN(dy); optional bf16 copy; optional dgamma/dbeta (fixed-order two-stage
+ * reduction; `accumulate` adds into them). partial_ws: 2*D*mfk_ln_bwd_ctas(M) floats. g_in may alias g_out. */
+int mfk_ln_bwd_ctas(int M);
+int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma,
+                      float* dbeta, float* partial_ws, int accumulate, int M, int D, void* stream);
+/* out[N] (+)= column sums of x[M,N] (bias gradients). partial_ws: 32*N floats. */
+int mfk_colsum(const void* x, int is_bf16, long long ld, int M, int N, float* out, float* partial_ws,
+               int accumulate, void* stream);
+
+/* ------------------------------------------------------------------ token assembly / prompt splice
+ * conv1 16x16 stride 16 as im2col: img fp32 [B,3,S,S] -> bf16 [B*(S/16)^2, 768] (clip/model.py:514-518). */
+int mfk_patch_im2col(const float* img, void* out_bf16, int B, int S, void* stream);
+/* [cls+pos ; patch tokens+pos ; fp16-rounded shared_ctx] -> ln_pre (clip/model.py:522-544).
+ * x0_save (pre-LN, optional) and mean/rstd are kept for backward.                                      */
+int mfk_vis_assemble_lnpre(const float* tok, const float* cls, const float* pos, const float* shared_ctx,
+                           const float* gamma, const float* beta, float* x0_save, float* x, float* mean,
+                           float* rstd, int B, int T, int n_ctx, int D, float eps, void* stream);
+/* cat(prefix, ctx, suffix) + positional_embedding, first Te positions (trainers/maple.py:152-166,181-187,54). */
+int mfk_text_assemble(const float* prefix, const float* ctx, const float* suffix, const float* pos, float* x,
+                      int C, int Te, int n_ctx, int Tfull, int D, void* stream);
+/* x[b, row0+j, :] = fp16_round(prompt[j, :]) for all b (clip/model.py:320-349; `.half()` at 327,344). */
+int mfk_prompt_splice_fwd(float* x, const float* prompt, int N, int T, int row0, int n_ctx, int D, void* stream);
+/* dprompt[j,:] = sum_b (round_fp16 ? fp16_round(g[b,row0+j,:]) : g[...]) in batch order; if zero_rows the
+ * rows are then cleared in g and g_bf16 (the spliced-away outputs of the previous layer get no gradient). */
+int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int N, int T, int row0, int n_ctx, int D,
+                          int round_fp16, int zero_rows, void* stream);
+int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16, int R, int D, void* stream);
+/* out[N, ldo] = in[M, ldi]^T as bf16 (in fp32 or bf16); optional straight bf16 copy. Used to keep
+ * K-major copies of weights (dgrad) and of activations/gradients (wgrad of resblocks.11).             */
+int mfk_transpose_bf16(const void* in, int in_is_f32, long long ldi, void* out, long long ldo, void* copy,
+                       long long ldc, int M, int N, void* stream);
+int mfk_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+
+/* ------------------------------------------------------------------ prompt-learner projections (fp32)
+ * y[m,N] = x[m,K] W[N,K]^T + b (trainers/maple.py:194-215; m = n_ctx) and its backward.               */
+int mfk_linear_small_fwd(const float* x, const float* W, const float* b, float* y, int m, int N, int K,
+                         void* stream);
+int mfk_linear_small_bwd(const float* x, const float* W, const float* dy, float* dW, float* db,
+                         const float* dx_add, float* dx, int m, int N, int K, void* stream);
+
+/* ------------------------------------------------------------------ logits + loss head (trainers/maple.py:325-372)
+ * label == NULL: inference, only `logits` [B,C] is written. Otherwise also loss[1], d_img[B,E], d_txt[C,E].
+ * ws: mfk_head_workspace_floats(B,C,E) floats.                                                         */
+long long mfk_head_workspace_floats(int B, int C, int E);
+int mfk_head_forward_backward(const float* img_feat, const float* txt_feat, const float* logit_scale,
+                              const long long* label, float* logits, float* loss, float* d_img, float* d_txt,
+                              float* ws, int B, int C, int E, void* stream);
+
+/* ------------------------------------------------------------------ FedAvg (trainers/maple_fed.py:309-325)
+ * client_ptrs_dev: device array of K device pointers, each to n elements (fp32, or fp16 if in_is_fp16).
+ * weights_dev: NULL = uniform (reference behaviour, divisor = K), else K floats (sample counts, divisor =
+ * their sum). flags_dev (optional, K ints, caller zeroes): bit0 = client had NaN, bit1 = client had Inf.  */
+int mfk_fedavg_reduce(const void* const* client_ptrs_dev, const float* weights_dev, float divisor, int K,
+                      long long n, int in_is_fp16, float* out_f32, void* out_f16, int* flags_dev, void* stream);
+/* check_weights_valid: ORs bit0 (NaN) / bit1 (Inf) into *flag_dev. dtype 0 f32, 1 f16, 2 bf16.       */
+int mfk_check_finite(const void* p, long long n, int dtype, int* flag_dev, void* stream);
+
+/* ------------------------------------------------------------------ clip_grad_norm_ + SGD (trainers/maple.py:592-598)
+ * norm_out[0] = ||g||_2 (fixed-order reduction; partial_ws: 296 floats).
+ * hyper_dev = {lr, momentum, dampening, weight_decay, max_norm, nesterov, first_step} as 7 floats.    */
+int mfk_grad_norm(const float* g, long long n, float* partial_ws, float* norm_out, void* stream);
+int mfk_sgd_step(float* p, float* g, float* mom, long long n, const float* hyper_dev,
+                 const float* total_norm_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFK_H_ */
