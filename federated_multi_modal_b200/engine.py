@@ -1,0 +1,499 @@
+"""MapleEngine — explicit forward/backward schedule of the MaPLe CustomCLIP step on libmfk kernels.
+
+This is the host side of the hot path: it owns the packed frozen CLIP
+weights (bf16, plus K-major transposes for dgrad), one flat fp32 arena with every trainable tensor
+(+ gradient and momentum arenas of the same layout), the saved activations, and issues the kernel
+sequence through the C ABI. It mirrors ``oracle/maple_cpu.py`` stage by stage; there is no autograd
+graph and no host synchronisation inside a step, so a step can be captured in a CUDA graph.
+
+Reference call sites replaced: CustomCLIP.forward (trainers/maple.py:304-381),
+MultiModalPromptLearner.forward (177-218), TextEncoder.forward (52-79),
+VisionTransformer_MaPLe.forward (clip/model.py:509-572), ResidualAttentionBlock_MaPLe.forward
+(clip/model.py:307-352) and loss.backward() (trainers/maple.py:590) for the reference's trainable
+set (trainers/maple.py:447-479) or the prompt-only set.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+_LIN = ("attn.in_proj", "attn.out_proj", "mlp.c_fc", "mlp.c_proj")
+
+
+def _lin_keys(name):
+    # nn.MultiheadAttention stores in_proj_weight / in_proj_bias; Linear stores .weight / .bias
+    if name == "attn.in_proj":
+        return "attn.in_proj_weight", "attn.in_proj_bias"
+    return name + ".weight", name + ".bias"
+
+
+class _Tower:
+    """Static description + packed weights + workspaces of one transformer tower."""
+
+    def __init__(self, name: str, D: int, heads: int, L: int, causal: bool):
+        self.name, self.D, self.heads, self.L, self.causal = name, D, heads, L, causal
+        self.w: List[Dict[str, torch.Tensor]] = []  # per layer packed tensors
+        self.N = self.T = self.M = 0
+        self.ws: Dict[str, torch.Tensor] = {}
+
+
+class MapleEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], tokenized_prompts: torch.Tensor, *, n_ctx: int = 2,
+                 depth: int = 9, device: str = "cuda", trainable: str = "reference", text_truncate: bool = True,
+                 patch: int = 16):
+        if not torch.cuda.is_available():
+            raise RuntimeError("MapleEngine needs a CUDA device: the libmfk kernels have no CPU fallback")
+        assert trainable in ("reference", "prompt_only")
+        self.dev = torch.device(device)
+        self.n, self.J, self.patch = n_ctx, depth, patch
+        self.trainable = trainable
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("clip_model2.")}
+        self.tok = tokenized_prompts.clone().cpu()
+        self.eot = self.tok.argmax(-1)
+        self.C = self.tok.shape[0]
+        self.Tfull = self.tok.shape[1]
+        self.Te = int(self.eot.max().item()) + 1 if text_truncate else self.Tfull
+        vD = sd["image_encoder.ln_pre.weight"].shape[0]
+        tD = sd["text_encoder.ln_final.weight"].shape[0]
+        vL = len({k.split(".")[3] for k in sd if k.startswith("image_encoder.transformer.resblocks.")})
+        tL = len({k.split(".")[3] for k in sd if k.startswith("text_encoder.transformer.resblocks.")})
+        self.vis = _Tower("image_encoder", vD, vD // 64, vL, False)
+        self.txt = _Tower("text_encoder", tD, tD // 64, tL, True)
+        self.E = sd["image_encoder.proj"].shape[1]
+        self.P = (sd["image_encoder.positional_embedding"].shape[0] - 1)  # patches per image
+        self.Tv = self.P + 1 + n_ctx
+        self._build_arena(sd)
+        self._pack_frozen(sd)
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._Bmax = 0
+        self._text_cache_valid = False
+        self.mom_initialized = False
+        self.repack_trainable()
+
+    # ------------------------------------------------------------------ parameters
+    def _trainable_names(self, sd) -> List[str]:
+        """Order of the arena: prompt learner | LayerNorms | resblocks.11 | never-updated."""
+        pl = [k for k in sd if k.startswith("prompt_learner.") and "token_" not in k and "proj_vis_to_lang" not in k]
+        ln = [k for k in sd if (".ln_" in k or "ln_pre." in k or "ln_post." in k or "ln_final." in k)]
+        last = []
+        for tw in (self.vis, self.txt):
+            pre = f"{tw.name}.transformer.resblocks.{tw.L - 1}."
+            if tw.L == 12:  # the reference unfreezes names containing "transformer.resblocks.11"
+                last += [k for k in sd if k.startswith(pre) and ".ln_" not in k]
+        tail = [k for k in sd if "proj_vis_to_lang" in k]  # trainable flag, never receives a gradient
+        self._n_pl = sum(sd[k].numel() for k in pl)
+        self._n_ln = sum(sd[k].numel() for k in ln)
+        self._n_last = sum(sd[k].numel() for k in last)
+        return pl + ln + last + tail
+
+    def _build_arena(self, sd):
+        names = self._trainable_names(sd)
+        total = sum(sd[k].numel() for k in names)
+        pad = (-total) % 64
+        self.params = torch.zeros(total + pad, device=self.dev, dtype=F32)
+        self.grads = torch.zeros_like(self.params)
+        self.momentum = torch.zeros_like(self.params)
+        self.p: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self.g: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self.offsets: "OrderedDict[str, tuple]" = OrderedDict()
+        off = 0
+        for k in names:
+            n = sd[k].numel()
+            # every tensor starts 16-byte aligned (all sizes are multiples of 4 elements)
+            assert off % 4 == 0, k
+            self.p[k] = self.params[off:off + n].view(sd[k].shape)
+            self.g[k] = self.grads[off:off + n].view(sd[k].shape)
+            self.p[k].copy_(sd[k].to(self.dev, F32))
+            self.offsets[k] = (off, n)
+            off += n
+        self.n_params_total = off
+        if self.trainable == "reference":
+            self.n_update = self._n_pl + self._n_ln + self._n_last
+        else:
+            self.n_update = self._n_pl
+        self.logit_scale = sd["logit_scale"].to(self.dev, F32).reshape(1).clone()
+        self.prefix = sd["prompt_learner.token_prefix"].to(self.dev, F32).contiguous()
+        self.suffix = sd["prompt_learner.token_suffix"].to(self.dev, F32).contiguous()
+
+    @property
+    def wgrad_last(self) -> bool:
+        return self.trainable == "reference" and self.vis.L == 12
+
+    def _pack_frozen(self, sd):
+        dev = self.dev
+        f32 = lambda k: sd[k].to(dev, F32).contiguous()
+        for tw in (self.vis, self.txt):
+            for l in range(tw.L):
+                pre = f"{tw.name}.transformer.resblocks.{l}."
+                w: Dict[str, torch.Tensor] = {}
+                for lin in _LIN:
+                    wk, bk = _lin_keys(lin)
+                    full_w, full_b = pre + wk, pre + bk
+                    if full_w in self.p:  # trainable master lives in the arena; bf16 copies made by repack
+                        W = self.p[full_w]
+                        w[lin + ".b"] = self.p[full_b]
+                        w[lin + ".master"] = W
+                        w[lin + ".w"] = torch.empty(W.shape, device=dev, dtype=BF16)
+                        w[lin + ".wT"] = torch.empty(W.shape[1], W.shape[0], device=dev, dtype=BF16)
+                    else:
+                        W = sd[full_w].to(dev, F32)
+                        w[lin + ".w"] = W.to(BF16).contiguous()
+                        w[lin + ".wT"] = W.t().to(BF16).contiguous()
+                        w[lin + ".b"] = f32(full_b)
+                for ln in ("ln_1", "ln_2"):
+                    w[ln + ".g"], w[ln + ".b"] = self.p[pre + ln + ".weight"], self.p[pre + ln + ".bias"]
+                tw.w.append(w)
+        v = "image_encoder."
+        conv = sd[v + "conv1.weight"].to(dev, F32)
+        self.conv_w = conv.reshape(conv.shape[0], -1).to(BF16).contiguous()
+        self.cls = f32(v + "class_embedding")
+        self.vpos = f32(v + "positional_embedding")
+        proj = sd[v + "proj"].to(dev, F32)
+        self.vproj = proj.to(BF16).contiguous()          # [768,512]  (B operand of the dgrad GEMM)
+        self.vproj_T = proj.t().to(BF16).contiguous()    # [512,768]  (B operand of the forward GEMM)
+        t = "text_encoder."
+        self.tpos = f32(t + "positional_embedding")
+        tp = sd[t + "text_projection"].to(dev, F32)
+        self.tproj = tp.to(BF16).contiguous()
+        self.tproj_T = tp.t().to(BF16).contiguous()
+        self.eot_rows = (torch.arange(self.C) * self.Te + self.eot).to(dev, torch.int32)
+
+    def repack_trainable(self):
+        """Refresh the bf16 (and transposed) copies of the trainable resblock weights from the fp32 arena."""
+        for tw in (self.vis, self.txt):
+            for w in tw.w:
+                for lin in _LIN:
+                    if lin + ".master" in w:
+                        ops.transpose_bf16(w[lin + ".master"], w[lin + ".wT"], w[lin + ".w"])
+        self._text_cache_valid = False
+
+    # ------------------------------------------------------------------ workspaces
+    def _buf(self, name, shape, dtype):
+        t = self._bufs.get(name)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(n, device=self.dev, dtype=dtype)
+            self._bufs[name] = t
+        return t[:n].view(shape)
+
+    def _tower_bufs(self, tw: _Tower, N: int, T: int, train: bool):
+        tw.N, tw.T, tw.M = N, T, N * T
+        M, D, L = tw.M, tw.D, tw.L
+        b = lambda n, s, d: self._buf(f"{tw.name}.{n}", s, d)
+        ws = tw.ws = {}
+        nl = L if train else 1
+        ws["x1"] = b("x1", (nl + 1, M, D), F32)   # x1[l] = input of layer l (after splice); x1[L] = output
+        ws["x2"] = b("x2", (nl, M, D), F32)       # x2[l] = after the attention residual
+        ws["h"] = b("h", (M, D), BF16)
+        ws["h2"] = b("h2", (M, D), BF16)
+        ws["qkv"] = b("qkv", (nl, M, 3 * D), BF16)
+        ws["att"] = b("att", (nl, M, D), BF16)
+        ws["act"] = b("act", (M, 4 * D), BF16)
+        if train:
+            ws["u"] = b("u", (L, M, 4 * D), BF16)
+            ws["lse"] = b("lse", (L, N * tw.heads * T), F32)
+            ws["stat"] = b("stat", (L, 4, M), F32)  # mean1, rstd1, mean2, rstd2
+            ws["g"] = b("g", (M, D), F32)
+            ws["g16"] = b("g16", (M, D), BF16)
+            ws["du"] = b("du", (M, 4 * D), BF16)
+            ws["dh"] = b("dh", (M, D), BF16)
+            ws["dqkv"] = b("dqkv", (M, 3 * D), BF16)
+            ws["delta"] = b("delta", (N * tw.heads * T,), F32)
+            ws["lnp"] = b("lnp", (2 * D * ops.ln_bwd_ctas(M),), F32)
+            ws["csum"] = b("csum", (32 * 4 * D,), F32)
+            if self.wgrad_last:
+                Mp = (M + 7) // 8 * 8
+                ws["tA"] = b("tA", (4 * D, Mp), BF16)
+                ws["tB"] = b("tB", (4 * D, Mp), BF16)
+
+    # ------------------------------------------------------------------ prompt learner
+    def _prompt_learner_fwd(self):
+        p, nd = self.p, self.J - 1
+        pl = "prompt_learner."
+        self.deep_text: List[torch.Tensor] = []
+        self.deep_vis: List[torch.Tensor] = []
+        for i in range(nd):
+            W, b = p[f"{pl}compound_prompt_projections.{i}.weight"], p[f"{pl}compound_prompt_projections.{i}.bias"]
+            if i % 2 == 0:
+                t = p[f"{pl}compound_prompts_text_parameters.{i // 2}"]
+                y = self._buf(f"pl.y{i}", (self.n, W.shape[0]), F32)
+                ops.linear_small_fwd(t, W, b, y)
+                self.deep_vis.append(y)
+                self.deep_text.append(t)
+            else:
+                v = p[f"{pl}visual_deep_prompts_parameters.{(i - 1) // 2}"]
+                y = self._buf(f"pl.y{i}", (self.n, W.shape[0]), F32)
+                ops.linear_small_fwd(v, W, b, y)
+                self.deep_text.append(y)
+                self.deep_vis.append(v)
+        self.shared = self._buf("pl.shared", (self.n, self.vis.D), F32)
+        ops.linear_small_fwd(p[pl + "ctx"], p[pl + "proj_lang_to_vis.weight"], p[pl + "proj_lang_to_vis.bias"],
+                             self.shared)
+
+    # ------------------------------------------------------------------ one residual block
+    def _slots(self, l: int, train: bool):
+        """(x1 in, x1 out, per-layer slot) — training keeps every layer, inference ping-pongs two buffers."""
+        return (l, l + 1, l) if train else (l % 2, (l + 1) % 2, 0)
+
+    def _block_fwd(self, tw: _Tower, l: int, train: bool):
+        ws, w = tw.ws, tw.w[l]
+        si, so, s = self._slots(l, train)
+        x1, x1n, x2 = ws["x1"][si], ws["x1"][so], ws["x2"][s]
+        st = ws["stat"][l] if train else (None, None, None, None)
+        ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_bf16=ws["h"], mean=st[0], rstd=st[1])
+        qkv, att = ws["qkv"][s], ws["att"][s]
+        ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=qkv)
+        ops.attn_fwd(qkv, att, ws["lse"][l] if train else None, tw.N, tw.T, tw.heads, tw.causal)
+        ops.gemm(att, w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=x1, out_f32=x2)
+        ops.layernorm_fwd(x2, w["ln_2.g"], w["ln_2.b"], y_bf16=ws["h2"], mean=st[2], rstd=st[3])
+        ops.gemm(ws["h2"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act"],
+                 out_pre=ws["u"][l] if train else None)
+        ops.gemm(ws["act"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=x2, out_f32=x1n)
+        return x1n
+
+    def _tower_fwd(self, tw: _Tower, deep: List[torch.Tensor], row0: int, train: bool):
+        out = None
+        for l in range(tw.L):
+            if l >= 1 and (l - 1) < len(deep):
+                ops.prompt_splice_fwd(tw.ws["x1"][self._slots(l, train)[0]], deep[l - 1], tw.N, tw.T, row0, self.n)
+            out = self._block_fwd(tw, l, train)
+        return out
+
+    def _wgrad(self, tw: _Tower, dy16, x16, dW, Nout, Kin):
+        """dW[Nout,Kin] = dy^T x via two K-major transposes and the same tcgen05 GEMM."""
+        ws, M = tw.ws, tw.M
+        Mp = (M + 7) // 8 * 8
+        tA = ws["tA"].view(-1)[:Nout * Mp].view(Nout, Mp)
+        tB = ws["tB"].view(-1)[:Kin * Mp].view(Kin, Mp)
+        ops.transpose_bf16(dy16, tA)
+        ops.transpose_bf16(x16, tB)
+        ops.gemm(tA, tB, out_f32=dW, k=M)
+
+    def _block_bwd(self, tw: _Tower, l: int):
+        ws, w, D, M = tw.ws, tw.w[l], tw.D, tw.M
+        g, g16 = ws["g"], ws["g16"]
+        st = ws["stat"][l]
+        pre = f"{tw.name}.transformer.resblocks.{l}."
+        wg = self.wgrad_last and l == tw.L - 1
+        ln_grads = self.trainable == "reference"
+        G = self.g
+        # ---- MLP branch
+        ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"])
+        if wg:
+            self._wgrad(tw, g16, ws["act"], G[pre + "mlp.c_proj.weight"], D, 4 * D)
+            ops.colsum(g, G[pre + "mlp.c_proj.bias"], ws["csum"])
+        ops.gemm(ws["du"], w["mlp.c_fc.wT"], out_bf16=ws["dh"])
+        if wg:
+            self._wgrad(tw, ws["du"], ws["h2"], G[pre + "mlp.c_fc.weight"], 4 * D, D)
+            ops.colsum(ws["du"], G[pre + "mlp.c_fc.bias"], ws["csum"])
+        ops.layernorm_bwd(ws["dh"], ws["x2"][l], st[2], st[3], w["ln_2.g"], g_in=g, g_out=g, g_out_bf16=g16,
+                          dgamma=G[pre + "ln_2.weight"] if ln_grads else None,
+                          dbeta=G[pre + "ln_2.bias"] if ln_grads else None, partial_ws=ws["lnp"])
+        # ---- attention branch
+        da = ws["dh"]
+        ops.gemm(g16, w["attn.out_proj.wT"], out_bf16=da)
+        if wg:
+            self._wgrad(tw, g16, ws["att"][l], G[pre + "attn.out_proj.weight"], D, D)
+            ops.colsum(g, G[pre + "attn.out_proj.bias"], ws["csum"])
+        ops.attn_bwd(ws["qkv"][l], ws["att"][l], da, ws["lse"][l], ws["delta"], ws["dqkv"], tw.N, tw.T, tw.heads,
+                     tw.causal)
+        ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"])
+        if wg:
+            self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)
+            ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
+        ops.layernorm_bwd(ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
+                          dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
+                          dbeta=G[pre + "ln_1.bias"] if ln_grads else None, partial_ws=ws["lnp"])
+
+    # ------------------------------------------------------------------ towers: embed + head rows
+    def _vision_embed(self, img: torch.Tensor, train: bool):
+        B = img.shape[0]
+        tw = self.vis
+        self._tower_bufs(tw, B, self.Tv, train)
+        col = self._buf("vis.col", (B * self.P, 3 * self.patch * self.patch), BF16)
+        tok = self._buf("vis.tok", (B * self.P, tw.D), F32)
+        ops.patch_im2col(img, col)
+        ops.gemm(col, self.conv_w, out_f32=tok)
+        p = self.p
+        x0 = self._buf("vis.x0", (tw.M, tw.D), F32) if train else None
+        self.vstat0 = self._buf("vis.stat0", (2, tw.M), F32)
+        ops.vis_assemble_lnpre(tok, self.cls, self.vpos, self.shared, p["image_encoder.ln_pre.weight"],
+                               p["image_encoder.ln_pre.bias"], x0, tw.ws["x1"][0], self.vstat0[0], self.vstat0[1], B,
+                               self.Tv, self.n)
+        self.vx0 = x0
+
+    def _features(self, tw: _Tower, xout, rows, ln_g, ln_b, projT, name, R, train):
+        y = self._buf(name + ".y", (R, tw.D), BF16)
+        xs = self._buf(name + ".xs", (R, tw.D), F32)
+        stat = self._buf(name + ".st", (2, R), F32)
+        ops.layernorm_fwd(xout, ln_g, ln_b, rowidx=rows, y_bf16=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
+        feat = self._buf(name + ".feat", (R, self.E), F32)
+        ops.gemm(y, projT, out_f32=feat)
+        return feat, xs, stat
+
+    def _text_features(self, train: bool):
+        tw, p = self.txt, self.p
+        self._tower_bufs(tw, self.C, self.Te, train)
+        ops.text_assemble(self.prefix, p["prompt_learner.ctx"], self.suffix, self.tpos, tw.ws["x1"][0], self.C,
+                          self.Te, self.n, self.Tfull)
+        xout = self._tower_fwd(tw, self.deep_text, 1, train)
+        return self._features(tw, xout, self.eot_rows, p["text_encoder.ln_final.weight"],
+                              p["text_encoder.ln_final.bias"], self.tproj_T, "txt", self.C, train)
+
+    def _image_features(self, img, train: bool):
+        tw, p = self.vis, self.p
+        self._vision_embed(img, train)
+        xout = self._tower_fwd(tw, self.deep_vis, self.Tv - self.n, train)
+        B = img.shape[0]
+        key = f"cls_rows{B}"
+        if key not in self._bufs:
+            self._bufs[key] = (torch.arange(B, device=self.dev, dtype=torch.int32) * self.Tv).contiguous()
+        self.cls_rows = self._bufs[key]
+        return self._features(tw, xout, self.cls_rows, p["image_encoder.ln_post.weight"],
+                              p["image_encoder.ln_post.bias"], self.vproj_T, "vis", B, train)
+
+    # ------------------------------------------------------------------ public: inference
+    @torch.no_grad()
+    def logits(self, img: torch.Tensor, cache_text: bool = True) -> torch.Tensor:
+        """Eval path of CustomCLIP.forward (trainers/maple.py:381): returns logits [B, C] (fp32).
+        Text features are input independent and cached across eval batches until parameters change."""
+        img = img.to(self.dev, F32).contiguous()
+        B = img.shape[0]
+        self._prompt_learner_fwd()
+        if not (cache_text and self._text_cache_valid):
+            ft, _, _ = self._text_features(False)
+            self._ft_cache = ft.clone()
+            self._text_cache_valid = True
+        fi, _, _ = self._image_features(img, False)
+        out = torch.empty(B, self.C, device=self.dev, dtype=F32)
+        ws = self._buf("head.ws", (ops.head_workspace_floats(B, self.C, self.E),), F32)
+        ops.head_forward_backward(fi, self._ft_cache, self.logit_scale, None, out, None, None, None, ws)
+        return out
+
+    # ------------------------------------------------------------------ public: training step
+    @torch.no_grad()
+    def forward_backward(self, img: torch.Tensor, label: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
+        """Forward + backward of one batch. Fills ``self.g[name]`` (fp32 arena) for every trainable tensor and
+        returns (loss[1], logits[B,C]) device tensors. No host synchronisation."""
+        assert img.is_cuda and img.dtype == F32 and label.is_cuda and label.dtype == torch.int64
+        B, C, n, nd = img.shape[0], self.C, self.n, self.J - 1
+        p, G = self.p, self.g
+        self._text_cache_valid = False
+        self._prompt_learner_fwd()
+        ft, txs, tstat = self._text_features(True)
+        fi, vxs, vstat = self._image_features(img, True)
+        logits = self._buf("head.logits", (B, C), F32)
+        loss = loss_out if loss_out is not None else self._buf("head.loss", (1,), F32)
+        dfi, dft = self._buf("head.dfi", (B, self.E), F32), self._buf("head.dft", (C, self.E), F32)
+        hws = self._buf("head.ws", (ops.head_workspace_floats(B, C, self.E),), F32)
+        ops.head_forward_backward(fi, ft, self.logit_scale, label, logits, loss, dfi, dft, hws)
+        ln_grads = self.trainable == "reference"
+
+        d_deep = {}
+        for tw, dfeat, proj, xs, stat, rows, lnname, R, deep_row0 in (
+                (self.vis, dfi, self.vproj, vxs, vstat, self.cls_rows, "image_encoder.ln_post", B, self.Tv - n),
+                (self.txt, dft, self.tproj, txs, tstat, self.eot_rows, "text_encoder.ln_final", C, 1)):
+            ws, D = tw.ws, tw.D
+            d16 = self._buf(tw.name + ".dfeat16", (R, self.E), BF16)
+            ops.cast_bf16(dfeat, d16)
+            dy = self._buf(tw.name + ".dy", (R, D), F32)
+            ops.gemm(d16, proj, out_f32=dy)
+            dxr = self._buf(tw.name + ".dxr", (R, D), F32)
+            ops.layernorm_bwd(dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=dxr,
+                              dgamma=G[lnname + ".weight"] if ln_grads else None,
+                              dbeta=G[lnname + ".bias"] if ln_grads else None, partial_ws=ws["lnp"], M=R)
+            ws["g"].zero_()
+            ws["g16"].zero_()
+            ops.scatter_rows(dxr, rows, ws["g"], ws["g16"])
+            dd = []
+            for l in reversed(range(tw.L)):
+                self._block_bwd(tw, l)
+                if l >= 1 and (l - 1) < nd:
+                    dp = self._buf(f"{tw.name}.dprompt{l - 1}", (n, D), F32)
+                    ops.prompt_splice_bwd(ws["g"], ws["g16"], dp, tw.N, tw.T, deep_row0, n, True, True)
+                    dd.append((l - 1, dp))
+            d_deep[tw.name] = dict(dd)
+
+        # ---- tower inputs
+        vws, tws = self.vis.ws, self.txt.ws
+        ops.layernorm_bwd(vws["g"], self.vx0, self.vstat0[0], self.vstat0[1], p["image_encoder.ln_pre.weight"],
+                          g_out=vws["g"], dgamma=G["image_encoder.ln_pre.weight"] if ln_grads else None,
+                          dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None, partial_ws=vws["lnp"])
+        d_shared = self._buf("pl.dshared", (n, self.vis.D), F32)
+        ops.prompt_splice_bwd(vws["g"], None, d_shared, B, self.Tv, self.Tv - n, n, True, False)
+        d_ctx_t = self._buf("pl.dctx_t", (n, self.txt.D), F32)
+        ops.prompt_splice_bwd(tws["g"], None, d_ctx_t, C, self.Te, 1, n, False, False)
+
+        # ---- prompt learner backward
+        pl = "prompt_learner."
+        dv, dt = d_deep[self.vis.name], d_deep[self.txt.name]
+        for i in range(nd):
+            Wn = f"{pl}compound_prompt_projections.{i}"
+            if i % 2 == 0:
+                pn = f"{pl}compound_prompts_text_parameters.{i // 2}"
+                ops.linear_small_bwd(p[pn], p[Wn + ".weight"], dv[i], dW=G[Wn + ".weight"], db=G[Wn + ".bias"],
+                                     dx_add=dt[i], dx=G[pn])
+            else:
+                pn = f"{pl}visual_deep_prompts_parameters.{(i - 1) // 2}"
+                ops.linear_small_bwd(p[pn], p[Wn + ".weight"], dt[i], dW=G[Wn + ".weight"], db=G[Wn + ".bias"],
+                                     dx_add=dv[i], dx=G[pn])
+        ops.linear_small_bwd(p[pl + "ctx"], p[pl + "proj_lang_to_vis.weight"], d_shared,
+                             dW=G[pl + "proj_lang_to_vis.weight"], db=G[pl + "proj_lang_to_vis.bias"],
+                             dx_add=d_ctx_t, dx=G[pl + "ctx"])
+        self.last = dict(image_features=fi, text_features=ft, dfi=dfi, dft=dft)
+        return loss, logits
+
+    # ------------------------------------------------------------------ optimizer
+    @torch.no_grad()
+    def sgd_step(self, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, dampening: float = 0.0,
+                 nesterov: bool = False, max_norm: float = 1.0, hyper: Optional[torch.Tensor] = None):
+        """clip_grad_norm_(max_norm) over all gradients + SGD on the updated region of the arena
+        (trainers/maple.py:592-598), then refresh bf16 copies of trainable block weights."""
+        n = self.n_update
+        ws = self._buf("opt.ws", (296,), F32)
+        norm = self._buf("opt.norm", (1,), F32)
+        if hyper is None:
+            hyper = torch.tensor([lr, momentum, dampening, weight_decay, max_norm, float(nesterov),
+                                  0.0 if self.mom_initialized else 1.0], device=self.dev, dtype=F32)
+        ops.grad_norm(self.grads[:n], ws, norm)
+        ops.sgd_step(self.params[:n], self.grads[:n], self.momentum[:n], hyper, norm, n)
+        self.mom_initialized = True
+        self.repack_trainable()
+        return norm
+
+    def reset_optimizer_state(self):
+        """broadcast_weights deletes every optimizer state entry (trainers/maple_fed.py:332-335)."""
+        self.momentum.zero_()
+        self.mom_initialized = False
+
+    # ------------------------------------------------------------------ state exchange
+    def trainable_state(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((k, v) for k, v in self.p.items())
+
+    def load_trainable(self, tensors: Dict[str, torch.Tensor]):
+        for k, v in tensors.items():
+            if k in self.p:
+                self.p[k].copy_(v.to(self.dev, F32))
+        self.repack_trainable()
+
+    def flops_per_step(self, B: int) -> float:
+        """Algorithmic FLOPs of one fwd+bwd step for the work actually performed."""
+        def tower(D, L, T, N, causal, wg):
+            lin = 2 * N * T * D * (3 * D + D + 4 * D + 4 * D)            # per layer fwd
+            att = 4 * N * T * T * D * ((T + 1) / (2 * T) if causal else 1.0)
+            fwd = L * (lin + att)
+            bwd = L * (lin + 2 * att) + (lin if wg else 0)
+            return fwd, bwd
+        vf, vb = tower(self.vis.D, self.vis.L, self.Tv, B, False, self.wgrad_last)
+        tf, tb = tower(self.txt.D, self.txt.L, self.Te, self.C, True, self.wgrad_last)
+        patch = 2 * B * self.P * self.vis.D * 3 * self.patch * self.patch
+        heads = 2 * 2 * (B * self.vis.D * self.E + self.C * self.txt.D * self.E)
+        return vf + vb + tf + tb + patch + heads
