@@ -46,7 +46,10 @@ class _Tower:
 class MapleEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], tokenized_prompts: torch.Tensor, *, n_ctx: int = 2,
                  depth: int = 9, device: str = "cuda", trainable: str = "reference", text_truncate: bool = True,
-                 patch: int = 16):
+                 patch: int = 16, share_from: Optional["MapleEngine"] = None):
+        """``share_from``: another engine on the same GPU (a co-located federated client). The frozen packed
+        CLIP weights and the activation workspaces are shared with it; only the trainable arena, its
+        gradient/momentum arenas and the bf16 copies of trainable block weights are per client."""
         if not torch.cuda.is_available():
             raise RuntimeError("MapleEngine needs a CUDA device: the libmfk kernels have no CPU fallback")
         assert trainable in ("reference", "prompt_only")
@@ -69,8 +72,8 @@ class MapleEngine:
         self.P = (sd["image_encoder.positional_embedding"].shape[0] - 1)  # patches per image
         self.Tv = self.P + 1 + n_ctx
         self._build_arena(sd)
-        self._pack_frozen(sd)
-        self._bufs: Dict[str, torch.Tensor] = {}
+        self._pack_frozen(sd, share_from)
+        self._bufs: Dict[str, torch.Tensor] = share_from._bufs if share_from is not None else {}
         self._Bmax = 0
         self._text_cache_valid = False
         self.mom_initialized = False
@@ -125,10 +128,11 @@ class MapleEngine:
     def wgrad_last(self) -> bool:
         return self.trainable == "reference" and self.vis.L == 12
 
-    def _pack_frozen(self, sd):
+    def _pack_frozen(self, sd, share_from=None):
         dev = self.dev
         f32 = lambda k: sd[k].to(dev, F32).contiguous()
         for tw in (self.vis, self.txt):
+            src_tw = None if share_from is None else (share_from.vis if tw is self.vis else share_from.txt)
             for l in range(tw.L):
                 pre = f"{tw.name}.transformer.resblocks.{l}."
                 w: Dict[str, torch.Tensor] = {}
@@ -141,6 +145,9 @@ class MapleEngine:
                         w[lin + ".master"] = W
                         w[lin + ".w"] = torch.empty(W.shape, device=dev, dtype=BF16)
                         w[lin + ".wT"] = torch.empty(W.shape[1], W.shape[0], device=dev, dtype=BF16)
+                    elif src_tw is not None and lin + ".master" not in src_tw.w[l]:
+                        for sfx in (".w", ".wT", ".b"):
+                            w[lin + sfx] = src_tw.w[l][lin + sfx]
                     else:
                         W = sd[full_w].to(dev, F32)
                         w[lin + ".w"] = W.to(BF16).contiguous()
@@ -149,6 +156,12 @@ class MapleEngine:
                 for ln in ("ln_1", "ln_2"):
                     w[ln + ".g"], w[ln + ".b"] = self.p[pre + ln + ".weight"], self.p[pre + ln + ".bias"]
                 tw.w.append(w)
+        t = "text_encoder."
+        self.eot_rows = (torch.arange(self.C) * self.Te + self.eot).to(dev, torch.int32)
+        if share_from is not None:
+            for a in ("conv_w", "cls", "vpos", "vproj", "vproj_T", "tpos", "tproj", "tproj_T"):
+                setattr(self, a, getattr(share_from, a))
+            return
         v = "image_encoder."
         conv = sd[v + "conv1.weight"].to(dev, F32)
         self.conv_w = conv.reshape(conv.shape[0], -1).to(BF16).contiguous()
@@ -157,12 +170,10 @@ class MapleEngine:
         proj = sd[v + "proj"].to(dev, F32)
         self.vproj = proj.to(BF16).contiguous()          # [768,512]  (B operand of the dgrad GEMM)
         self.vproj_T = proj.t().to(BF16).contiguous()    # [512,768]  (B operand of the forward GEMM)
-        t = "text_encoder."
         self.tpos = f32(t + "positional_embedding")
         tp = sd[t + "text_projection"].to(dev, F32)
         self.tproj = tp.to(BF16).contiguous()
         self.tproj_T = tp.t().to(BF16).contiguous()
-        self.eot_rows = (torch.arange(self.C) * self.Te + self.eot).to(dev, torch.int32)
 
     def repack_trainable(self):
         """Refresh the bf16 (and transposed) copies of the trainable resblock weights from the fp32 arena."""
@@ -182,12 +193,20 @@ class MapleEngine:
         if t is None or t.numel() < n or t.dtype != dtype:
             t = torch.empty(n, device=self.dev, dtype=dtype)
             self._bufs[name] = t
+            # CUDA graphs captured earlier hold raw pointers into the old buffers: bump the generation so
+            # their owners re-capture before the next replay (see MaPLe.forward_backward)
+            self._bufs["__generation__"] = self._bufs.get("__generation__", 0) + 1
         return t[:n].view(shape)
+
+    @property
+    def buffer_generation(self) -> int:
+        return self._bufs.get("__generation__", 0)
 
     def _tower_bufs(self, tw: _Tower, N: int, T: int, train: bool):
         tw.N, tw.T, tw.M = N, T, N * T
         M, D, L = tw.M, tw.D, tw.L
-        b = lambda n, s, d: self._buf(f"{tw.name}.{n}", s, d)
+        mode = "train" if train else "eval"  # separate pools: an eval batch never resizes training buffers
+        b = lambda n, s, d: self._buf(f"{tw.name}.{mode}.{n}", s, d)
         ws = tw.ws = {}
         nl = L if train else 1
         ws["x1"] = b("x1", (nl + 1, M, D), F32)   # x1[l] = input of layer l (after splice); x1[L] = output
@@ -378,6 +397,9 @@ class MapleEngine:
         ops.head_forward_backward(fi, self._ft_cache, self.logit_scale, None, out, None, None, None, ws)
         return out
 
+    def last_image_features(self) -> torch.Tensor:
+        return self._bufs["vis.feat"].view(-1)[: self.vis.N * self.E].view(self.vis.N, self.E).clone()
+
     # ------------------------------------------------------------------ public: training step
     @torch.no_grad()
     def forward_backward(self, img: torch.Tensor, label: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
@@ -473,6 +495,14 @@ class MapleEngine:
         """broadcast_weights deletes every optimizer state entry (trainers/maple_fed.py:332-335)."""
         self.momentum.zero_()
         self.mom_initialized = False
+
+    def round_frozen_to_fp16(self):
+        """The reference's FedAvg casts EVERY averaged tensor to fp16 (trainers/maple_fed.py:314), so after the
+        first aggregation its fp32 frozen tensors (class/positional embeddings, logit_scale) hold fp16-rounded
+        values. Idempotent; shared tensors of co-located clients are rounded once."""
+        for t in (self.cls, self.vpos, self.tpos, self.logit_scale):
+            t.copy_(t.half().float())
+        self._text_cache_valid = False
 
     # ------------------------------------------------------------------ state exchange
     def trainable_state(self) -> "OrderedDict[str, torch.Tensor]":

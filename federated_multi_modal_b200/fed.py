@@ -1,0 +1,115 @@
+"""Round-end exchange for FedAvg over one 8xB200 NVLink/NVSwitch box.
+
+One process per GPU. Clients are assigned to ranks in contiguous blocks (rank r owns clients
+[r*k, (r+1)*k)), so rank-major gather order == client order and the fixed-order reduction
+(`mfk_fedavg_reduce`) gives bit-identical results on every rank, for any number of GPUs.
+
+Transports for the client tensors (flat fp32 arenas of the trainable parameters):
+  "p2p"  — symmetric-memory buffers: every rank's reduce kernel loads the peers' rows straight over
+           NVLink (peer pointers in the kernel's pointer table), i.e. transfer and weighted reduction are
+           ONE kernel; a symmetric-memory barrier on each side orders it against the producers.
+  "nccl" — torch.distributed all_gather_into_tensor, then the same reduce kernel on local rows
+           (also the path used with the gloo backend in CPU tests of the host logic).
+No ring/tree all-reduce is used: its summation order differs from the reference's (not bit-exact).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def dist_info() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def clients_of_rank(num_clients: int, rank: int, world: int) -> List[int]:
+    """Contiguous block assignment; requires num_clients % world == 0 (BASELINE configs 3/4: 8/8, 32/{2,4,8})."""
+    if num_clients % world != 0:
+        raise ValueError(f"num_clients={num_clients} must be a multiple of world size {world}")
+    k = num_clients // world
+    return list(range(rank * k, (rank + 1) * k))
+
+
+class FedAvgExchange:
+    def __init__(self, n: int, k_local: int, device, transport: str = "auto"):
+        self.rank, self.world = dist_info()
+        self.n, self.k_local, self.K = n, k_local, k_local * self.world
+        self.dev = torch.device(device)
+        self.transport = transport
+        self._symm = None
+        cuda = self.dev.type == "cuda"
+        if transport == "auto":
+            self.transport = "p2p" if (cuda and self.world > 1 and dist.get_backend() == "nccl") else "nccl"
+        if self.transport == "p2p" and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.send = symm_mem.empty(k_local * n, device=self.dev, dtype=torch.float32)
+                self._symm = symm_mem.rendezvous(self.send, dist.group.WORLD)
+                self.send = self.send.view(k_local, n)
+            except Exception as e:  # noqa: BLE001 — symmetric memory unavailable: use the NCCL transport
+                print(f"[fed] symmetric memory unavailable ({type(e).__name__}: {e}); using nccl all_gather")
+                self.transport = "nccl"
+        if self._symm is None:
+            self.send = torch.zeros(k_local, n, device=self.dev, dtype=torch.float32)
+        self.gathered = None if self._symm is not None else torch.zeros(self.K, n, device=self.dev,
+                                                                         dtype=torch.float32)
+        self.status_local = torch.zeros(k_local, 2, device=self.dev, dtype=torch.float32)  # [ok, n_samples]
+        self.status = torch.zeros(self.K, 2, device=self.dev, dtype=torch.float32)
+        if cuda:
+            self.out32 = torch.zeros(n, device=self.dev, dtype=torch.float32)
+            self.out16 = torch.zeros(n, device=self.dev, dtype=torch.float16)
+            self.flags = torch.zeros(self.K, device=self.dev, dtype=torch.int32)
+
+    # -------------------------------------------------------------------- stage 1: publish + gather
+    def publish(self, j: int, arena: torch.Tensor, ok: bool = True, n_samples: float = 1.0):
+        self.send[j].copy_(arena[: self.n])
+        self.status_local[j, 0] = 1.0 if ok else 0.0
+        self.status_local[j, 1] = float(n_samples)
+
+    def gather(self) -> List[torch.Tensor]:
+        """Returns the K client rows in client order (views; peer memory for the p2p transport)."""
+        if self.world == 1:
+            self.status.copy_(self.status_local)
+            return [self.send[j] for j in range(self.k_local)]
+        dist.all_gather_into_tensor(self.status.view(-1), self.status_local.view(-1))
+        if self._symm is not None:
+            self._symm.barrier()
+            rows = []
+            for r in range(self.world):
+                peer = self._symm.get_buffer(r, (self.k_local, self.n), torch.float32)
+                rows += [peer[j] for j in range(self.k_local)]
+            return rows
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.send.view(-1))
+        return [self.gathered[k] for k in range(self.K)]
+
+    # -------------------------------------------------------------------- stage 2: fixed-order reduce (CUDA)
+    def reduce(self, rows: Sequence[torch.Tensor], weighted: bool = False):
+        """-> (mean fp32 [n], mean fp16 [n], valid client ids, per-client NaN/Inf flags[K]). Invalid clients
+        (failed locally, or NaN/Inf in their tensors — check_weights_valid, trainers/maple_fed.py:271-277)
+        are excluded; the divisor is the number (or sample count) of the valid ones."""
+        from . import ops
+        status = self.status.cpu()
+        # validity scan of every client's tensor (device side, one flag word per client)
+        self.flags.zero_()
+        for k, r in enumerate(rows):
+            ops.check_finite(r, self.flags[k:k + 1])
+        if self._symm is not None:
+            pass
+        bad = self.flags.cpu()
+        valid = [k for k in range(self.K) if status[k, 0] > 0 and int(bad[k]) == 0]
+        if not valid:
+            return None, None, valid, bad
+        ptrs = torch.tensor([rows[k].data_ptr() for k in valid], dtype=torch.int64, device=self.dev)
+        if weighted:
+            w = torch.tensor([float(status[k, 1]) for k in valid], dtype=torch.float32, device=self.dev)
+            div = float(sum(float(status[k, 1]) for k in valid))
+        else:
+            w, div = None, float(len(valid))
+        ops.fedavg_reduce(ptrs, w, div, len(valid), self.n, False, self.out32, self.out16, None)
+        if self._symm is not None:
+            self._symm.barrier()  # peers may overwrite their send buffers only after everyone has read them
+        return self.out32, self.out16, valid, bad

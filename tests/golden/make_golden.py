@@ -129,3 +129,18 @@ if __name__ == "__main__":
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+def state_dict_spec():
+    """Key / shape / dtype list of the reference CustomCLIP.state_dict() in its default fp16 mode, and the
+    names its freeze policy leaves trainable -> tests/golden/state_dict_spec.pt (drop-in compatibility pin)."""
+    cfg = synth.make_cfg()
+    m = rh.build_reference_customclip(synth.random_clip_state_dict(0), synth.synthetic_classnames(10), cfg,
+                                      synth.random_prompt_learner_state(1), fp32=False)
+    spec = [(k, tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()]
+    train = sorted(n for n, p in m.named_parameters() if p.requires_grad)
+    torch.save(dict(spec=spec, trainable=train), os.path.join(HERE, "state_dict_spec.pt"))
+
+
+if __name__ == "__main__":
+    state_dict_spec()

@@ -1,0 +1,147 @@
+"""CPU: the drop-in surface (names, signatures, state_dict layout, C ABI symbols, host logic)."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import load_golden, REPO
+from federated_multi_modal_b200 import synth
+
+
+def _model(C=10):
+    from federated_multi_modal_b200.clip import build_model
+    from federated_multi_modal_b200.trainers import CustomCLIP
+    dd = {"trainer": "MaPLe", "vision_depth": 0, "language_depth": 0, "vision_ctx": 0, "language_ctx": 0,
+          "maple_length": 2}
+    clip = build_model(synth.random_clip_state_dict(0), dd)
+    return CustomCLIP(synth.make_cfg(), synth.synthetic_classnames(C), clip)
+
+
+def test_state_dict_layout_matches_reference():
+    spec = load_golden("state_dict_spec.pt")
+    m = _model()
+    sd = torch.nn.Module.state_dict(m)
+    ours = [(k, tuple(v.shape), str(v.dtype)) for k, v in sd.items()]
+    assert ours == spec["spec"]  # same 634 keys, same order, shapes and dtypes as the reference in fp16 mode
+
+
+def test_freeze_policy_matches_reference():
+    from federated_multi_modal_b200.trainers.maple import MaPLe
+    spec = load_golden("state_dict_spec.pt")
+    m = _model()
+    # the policy of MaPLe.build_model, applied without moving to a device
+    for p in m.parameters():
+        p.requires_grad_(False)
+    for n, p in m.named_parameters():
+        if "prompt_learner" in n or "transformer.resblocks.11" in n:
+            p.requires_grad_(True)
+    for _, mod in m.named_modules():
+        if isinstance(mod, torch.nn.LayerNorm):
+            for p in mod.parameters():
+                p.requires_grad_(True)
+    ours = sorted(n for n, p in m.named_parameters() if p.requires_grad)
+    assert ours == spec["trainable"] and len(ours) == 147
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 14250496
+    src = inspect.getsource(MaPLe.build_model)
+    assert "transformer.resblocks.11" in src and "prompt_learner" in src
+
+
+def test_signatures_match_reference_surface():
+    from federated_multi_modal_b200.clip import model as cm
+    from federated_multi_modal_b200.trainers import (ClientDataManager, CustomCLIP, MaPLe, MaPLeFederated,
+                                                     MultiModalPromptLearner, TextEncoder, partition_dataset_iid)
+    def args(f):
+        return list(inspect.signature(f).parameters)
+    assert args(CustomCLIP.forward) == ["self", "image", "label", "caption", "return_feature"]
+    assert args(CustomCLIP.__init__) == ["self", "cfg", "classnames", "clip_model"]
+    assert args(MultiModalPromptLearner.__init__) == ["self", "cfg", "classnames", "clip_model"]
+    assert args(TextEncoder.forward) == ["self", "prompts", "tokenized_prompts", "compound_prompts_deeper_text"]
+    assert args(cm.VisionTransformer_MaPLe.forward) == ["self", "x", "shared_ctx", "compound_deeper_prompts",
+                                                        "clip_embeddings"]
+    assert args(cm.ResidualAttentionBlock_MaPLe.__init__) == ["self", "d_model", "n_head", "attn_mask",
+                                                              "design_details", "text_layer", "i"]
+    assert args(cm.build_model) == ["state_dict", "design_details"]
+    assert args(ClientDataManager.__init__)[:5] == ["self", "train_x", "val", "test", "cfg"]
+    assert args(partition_dataset_iid) == ["dataset", "num_clients"]
+    for name in ("forward_backward", "parse_batch_train", "run_epoch", "update_lr", "test", "load_model",
+                 "build_model", "check_cfg", "model_inference"):
+        assert hasattr(MaPLe, name)
+    for name in ("train", "safe_average_weights", "check_weights_valid", "broadcast_weights", "save_model",
+                 "load_model", "finalize_training"):
+        assert hasattr(MaPLeFederated, name)
+    assert args(MaPLeFederated.safe_average_weights) == ["self", "local_dicts", "valid_clients"]
+
+
+def test_no_cpu_fallback():
+    m = _model().train()
+    img, lab = synth.make_batch(2, 10)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(img, lab)
+    from federated_multi_modal_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(32, 8, dtype=torch.bfloat16),
+                 out_f32=torch.zeros(8, 32))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from federated_multi_modal_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(REPO, "include", "mfk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mfk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mfk_version() >= 100
+    assert b"invalid argument" in lib.mfk_error_string(-1)
+    # argument validation happens before any CUDA call, so it can be exercised without a GPU
+    assert lib.mfk_gemm_bf16(None, 0, None, 0, 0, 0, 0, None, 0, None, 0, None, 0, None, 0, None, 0, None, 0, 0,
+                             None) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "federated_multi_modal_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("oracle/maple_cpu.py", ""), os.path.join(root, f)
+
+
+def test_lr_schedule_restates_dassl_constant_warmup_cosine():
+    from federated_multi_modal_b200.dassl_compat import ConstantWarmupCosine
+
+    class H:
+        lr = 0.0
+    h = H()
+    s = ConstantWarmupCosine(0.0026, 2, 1, 1e-4, h)
+    seq = [h.lr]
+    for _ in range(3):
+        s.step(); seq.append(h.lr)
+    assert seq == pytest.approx([1e-4, 0.0026, 0.0013, 0.0], abs=1e-12)
+    # the reference rebuilds the scheduler every round and sets last_epoch = epoch - 1 (maple_fed.py:337-339)
+    h = H(); s = ConstantWarmupCosine(0.0026, 2, 1, 1e-4, h); s.last_epoch = 9
+    seq = [h.lr]
+    for _ in range(2):
+        s.step(); seq.append(h.lr)
+    assert seq == pytest.approx([1e-4, 0.0013, 0.0], abs=1e-12)
+
+
+def test_partitioners():
+    from types import SimpleNamespace
+    from federated_multi_modal_b200.trainers import Datum, partition_dataset_dirichlet, partition_dataset_iid
+    from federated_multi_modal_b200.trainers.data_partition import dirichlet_label_split
+    items = [Datum(label=i % 7, classname=f"c{i % 7}") for i in range(700)]
+    ds = SimpleNamespace(train_x=items, val=[1], test=[2])
+    parts = partition_dataset_iid(ds, 3)
+    assert [len(p[0]) for p in parts] == [233, 233, 234] and parts[0][1] == [1] and parts[2][2] == [2]
+    assert sorted(id(x) for p in parts for x in p[0]) == sorted(id(x) for x in items)
+    a = dirichlet_label_split([it.label for it in items], 8, 0.5, seed=0)
+    b = dirichlet_label_split([it.label for it in items], 8, 0.5, seed=0)
+    assert a == b and sorted(i for p in a for i in p) == list(range(700))
+    sizes = [len(p) for p in a]
+    assert max(sizes) > 1.5 * min(sizes)  # label skew gives unequal clients
+    d = partition_dataset_dirichlet(ds, 8, 0.5, 0)
+    assert sum(len(p[0]) for p in d) == 700

@@ -1,0 +1,142 @@
+"""GPU: the drop-in trainer surface (CustomCLIP autograd bridge, MaPLe.forward_backward, MaPLeFederated)."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import load_golden
+from federated_multi_modal_b200 import synth
+
+if torch.cuda.is_available():
+    from federated_multi_modal_b200.trainers import (ClientDataManager, CustomCLIP, MaPLe, MaPLeFederated)
+    from federated_multi_modal_b200.trainers.client_datamanager import synthetic_client_items
+    from federated_multi_modal_b200.trainers.data_partition import dirichlet_label_split
+    from federated_multi_modal_b200.clip import build_model
+    from oracle.maple_cpu import fedavg_oracle
+
+DD = {"trainer": "MaPLe", "vision_depth": 0, "language_depth": 0, "vision_ctx": 0, "language_ctx": 0,
+      "maple_length": 2}
+
+
+def _custom_clip(C=10):
+    clip = build_model(synth.random_clip_state_dict(0), DD)
+    m = CustomCLIP(synth.make_cfg(), synth.synthetic_classnames(C), clip)
+    m.prompt_learner.load_state_dict(synth.random_prompt_learner_state(1), strict=False)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    for n, p in m.named_parameters():
+        if "prompt_learner" in n or "transformer.resblocks.11" in n:
+            p.requires_grad_(True)
+    for _, mod in m.named_modules():
+        if isinstance(mod, torch.nn.LayerNorm):
+            for p in mod.parameters():
+                p.requires_grad_(True)
+    return m.cuda()
+
+
+def test_customclip_autograd_bridge_and_eval():
+    G = load_golden("c1_fp32.pt")
+    img, lab = synth.make_batch(4, 10, 123)
+    m = _custom_clip()
+    m.eval()
+    lg = m(img.cuda())
+    # the module holds the reference's fp16 prompt-learner dtypes, so compare at the bf16 tolerance
+    assert (lg.cpu() - G["logits_eval"]).abs().max().item() < 2e-2 * G["logits_eval"].abs().max().item()
+    m.train()
+    loss = m(img.cuda(), lab.cuda())
+    assert loss.requires_grad and abs(loss.item() - G["loss"].item()) < 2e-2 * G["loss"].item()
+    loss.backward()
+    got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert len(got) == 145
+    for n, g in got.items():
+        assert torch.equal(g.float(), m.engine.g[n].to(g.dtype).float()), n
+    # a torch optimiser step changes the parameters; the engine picks the new values up
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.01)
+    opt.step()
+    l2 = m(img.cuda(), lab.cuda())
+    assert l2.item() != loss.item()
+
+
+def _trainer(graph, B=4, C=10):
+    cfg = synth.make_cfg()
+    cfg.USE_CUDA_GRAPH = graph
+    t = MaPLe(cfg, client_id=0, classnames=synth.synthetic_classnames(C))
+    t.model.prompt_learner.load_state_dict(synth.random_prompt_learner_state(1), strict=False)
+    t.model.load_state_dict(torch.nn.Module.state_dict(t.model))  # push the loaded values into the engine
+    return t
+
+
+def test_maple_forward_backward_graph_equals_eager_and_learns():
+    img, lab = synth.make_batch(4, 10, 123)
+    batch = {"img": img.pin_memory(), "label": lab.pin_memory()}
+    losses = {}
+    params = {}
+    for graph in (False, True):
+        t = _trainer(graph)
+        t.model.train()
+        losses[graph] = [t.forward_backward(batch)["loss"] for _ in range(4)]
+        params[graph] = t.model.engine.params.clone()
+        assert len(t.grad_norms) == 4 and all(0 < g <= 1.0 for g in t.grad_norms)
+    assert losses[True] == losses[False]            # CUDA-graph replay is bit-identical to eager launches
+    assert torch.equal(params[True], params[False])
+    assert losses[True][-1] < losses[True][0]       # the step trains
+    # state_dict() reflects the fused optimiser's updates, in the reference's dtypes
+    sd = t.model.state_dict()
+    assert sd["prompt_learner.ctx"].dtype == torch.float16
+    assert torch.equal(sd["prompt_learner.compound_prompts_text_parameters.0"],
+                       t.model.engine.p["prompt_learner.compound_prompts_text_parameters.0"])
+
+
+def test_maple_rejects_bad_input_like_reference():
+    t = _trainer(False)
+    img, lab = synth.make_batch(4, 10, 123)
+    img[0, 0, 0, 0] = float("nan")
+    with pytest.raises(ValueError, match="NaN"):
+        t.forward_backward({"img": img, "label": lab})
+
+
+def test_federated_rounds_single_gpu_bit_exact_average():
+    C, K = 10, 2
+    cfg = synth.make_cfg()
+    cfg.FED.NUM_CLIENTS, cfg.FED.NUM_ROUNDS, cfg.FED.LOCAL_EPOCHS = K, 2, 1
+    cfg.DATALOADER = synth._NS(TRAIN_X=synth._NS(BATCH_SIZE=4), TEST=synth._NS(BATCH_SIZE=8))
+    cfg.OUTPUT_DIR = ""
+    names = synth.synthetic_classnames(C)
+    pool = synthetic_client_items(C, 2, seed=0, classnames=names)  # 20 images
+    parts = dirichlet_label_split([it.label for it in pool], K, alpha=0.5, seed=0, min_size=4)
+    test_items = pool[:8]
+    dms = [ClientDataManager([pool[i] for i in p], [], test_items, cfg) for p in parts]
+    fed = MaPLeFederated(cfg, client_data_managers=dms, classnames=names)
+    assert len(fed.clients) == K
+    # co-located clients share the frozen weights and workspaces
+    e0, e1 = fed.clients[0].model.engine, fed.clients[1].model.engine
+    assert e0.vis.w[0]["mlp.c_fc.w"].data_ptr() == e1.vis.w[0]["mlp.c_fc.w"].data_ptr()
+    assert e0.params.data_ptr() != e1.params.data_ptr()
+    # instrument one aggregation: capture what the clients publish
+    captured = {}
+    orig = fed._aggregate
+    def spy():
+        captured["rows"] = [r.clone().cpu() for r in fed.exchange.gather()]
+        return orig()
+    fed._aggregate = spy
+    fed.train()
+    assert fed.nan_stats["total_updates"] == 2 and len(fed.round_times) == 2
+    n = e0.n_update
+    mean32, mean16 = fedavg_oracle(captured["rows"])
+    assert torch.equal(fed.last_mean_fp32.cpu(), mean32)            # FedAvg'd tensors bit-exact in fp32
+    assert torch.equal(fed.global_arena.cpu(), mean16.float())      # and the reference's .half() applied
+    for t in fed.clients:                                           # broadcast reached every client
+        assert torch.equal(t.model.engine.params[:n], fed.global_arena)
+        assert not t.model.engine.mom_initialized                   # optimiser state dropped
+    # reference-signature utilities on full state_dicts
+    sds = [{k: v.clone() for k, v in t.model.state_dict().items()} for t in fed.clients]
+    assert fed.check_weights_valid(sds[0])
+    avg = fed.safe_average_weights(sds, K)
+    assert set(avg) == set(sds[0]) and all(v.dtype == torch.float16 for v in avg.values())
+    k = "prompt_learner.compound_prompts_text_parameters.1"
+    assert torch.equal(avg[k].cpu(), fedavg_oracle([s[k].cpu() for s in sds])[1])
+    sds[1][k][0, 0] = float("inf")
+    assert not fed.check_weights_valid(sds[1])
+    fed.broadcast_weights(avg)
