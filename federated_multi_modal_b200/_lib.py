@@ -49,7 +49,8 @@ _NO_STATUS = {"mfk_version", "mfk_error_string", "mfk_head_workspace_floats", "m
 
 _lock = threading.Lock()
 _lib = None
-launch_count = 0  # number of C-ABI kernel-launching calls made (bench.py reports it)
+launch_count = 0  # C-ABI calls that launched work
+kernel_count = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:
@@ -82,15 +83,17 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args):
-    """Invoke a C-ABI entry point; tensors are passed as raw pointers. Raises on non-zero status."""
-    global launch_count
+def call(name: str, *args, kernels: int = 1):
+    """Invoke a C-ABI entry point; tensors are passed as raw pointers. Raises on non-zero status.
+    ``kernels`` = number of CUDA kernels this call launches (for the launch accounting only)."""
+    global launch_count, kernel_count
     lib = load()
     conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
     rc = getattr(lib, name)(*conv)
     if name in _NO_STATUS:
         return rc
     launch_count += 1
+    kernel_count += kernels
     if rc != 0:
         msg = lib.mfk_error_string(rc)
         raise RuntimeError(f"{name} failed with status {rc}: {msg.decode() if msg else '?'}")

@@ -50,9 +50,9 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 __device__ __forceinline__ float q16(float x) { return __half2float(__float2half_rn(x)); }
 
 // QuickGELU (clip/model.py:162-164) and its derivative
-__device__ __forceinline__ float quickgelu(float u) { return u / (1.0f + __expf(-1.702f * u)); }
+__device__ __forceinline__ float quickgelu(float u) { return __fdividef(u, 1.0f + __expf(-1.702f * u)); }
 __device__ __forceinline__ float dquickgelu(float u) {
-  float s = 1.0f / (1.0f + __expf(-1.702f * u));
+  float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * u));
   return s * (1.0f + 1.702f * u * (1.0f - s));
 }
 
@@ -97,6 +97,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// smem (staged, swizzled) -> global tile store; completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
@@ -186,3 +194,6 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a
 // Host: encode a 2-D bf16 row-major tensor map with 128-byte swizzle (box inner = 64 elements).
 int mfk_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                           uint32_t box_rows, uint32_t box_cols);
+// General form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 64 or 128 (= box_cols * elem_bytes).
+int mfk_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                     uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);

@@ -150,14 +150,26 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
   }
 }
 
-// out[c] (+)= sum_p partial[p, c]  (fixed order p = 0..P-1)
+// out[c] (+)= sum_p partial[p, c]. block (32, 8): 8 row groups sum P/8 partials each (strided, fixed order),
+// then a fixed-order 8-way combine. Two outputs (dgamma | dbeta) are handled by blockIdx.y.
 __global__ void partial_reduce_kernel(const float* __restrict__ partial, int P, int N, long long pstride,
-                                      float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+                                      long long ystride, float* __restrict__ out0, float* __restrict__ out1,
+                                      int accumulate) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float* out = blockIdx.y == 0 ? out0 : out1;
+  const float* src = partial + (size_t)blockIdx.y * ystride;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += partial[(size_t)p * pstride + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < N && out)
+    for (int p = threadIdx.y; p < P; p += 8) s += src[(size_t)p * pstride + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N && out) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // ============================================================================ column sums (bias grads)
@@ -370,14 +382,21 @@ __global__ void linear_small_bwd_w_kernel(const float* __restrict__ x, const flo
     db[n] = s;
   }
 }
+// block (32, 8): 32 consecutive k per block, 8 groups stride over n; fixed-order combine. grid (K/32, m).
 __global__ void linear_small_bwd_x_kernel(const float* __restrict__ W, const float* __restrict__ dy,
                                           const float* __restrict__ add, float* __restrict__ dx, int m, int N, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  for (int r = 0; r < m; ++r) {
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += dy[(size_t)r * N + n] * W[(size_t)n * K + k];
-    dx[(size_t)r * K + k] = s + (add ? add[(size_t)r * K + k] : 0.f);
+  __shared__ float red[8][33];
+  const int k = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y;
+  float s = 0.f;
+  if (k < K)
+    for (int n = threadIdx.y; n < N; n += 8) s += dy[(size_t)r * N + n] * W[(size_t)n * K + k];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    dx[(size_t)r * K + k] = t + (add ? add[(size_t)r * K + k] : 0.f);
   }
 }
 
@@ -427,9 +446,8 @@ extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
 #undef LNB
   MFK_CHECK_LAUNCH();
   if (part) {
-    const int tb = 128;
-    if (dgamma) partial_reduce_kernel<<<(D + tb - 1) / tb, tb, 0, ST(stream)>>>(part, grid, D, 2LL * D, dgamma, accumulate);
-    if (dbeta) partial_reduce_kernel<<<(D + tb - 1) / tb, tb, 0, ST(stream)>>>(part + D, grid, D, 2LL * D, dbeta, accumulate);
+    partial_reduce_kernel<<<dim3((D + 31) / 32, 2), dim3(32, 8), 0, ST(stream)>>>(part, grid, D, 2LL * D, D, dgamma,
+                                                                                  dbeta, accumulate);
     MFK_CHECK_LAUNCH();
   }
   return MFK_OK;
@@ -442,7 +460,8 @@ extern "C" int mfk_colsum(const void* x, int is_bf16, long long ld, int M, int N
   dim3 grid((N + 63) / 64, P), block(32, 8);
   if (is_bf16) colsum_partial_kernel<true><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
   else colsum_partial_kernel<false><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
-  partial_reduce_kernel<<<(N + 127) / 128, 128, 0, ST(stream)>>>(partial_ws, P, N, N, out, accumulate);
+  partial_reduce_kernel<<<dim3((N + 31) / 32, 1), dim3(32, 8), 0, ST(stream)>>>(partial_ws, P, N, N, 0, out, nullptr,
+                                                                                accumulate);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -532,7 +551,7 @@ extern "C" int mfk_linear_small_bwd(const float* x, const float* W, const float*
                                     const float* dx_add, float* dx, int m, int N, int K, void* stream) {
   if (!x || !W || !dy || m <= 0) return MFK_EARG;
   if (dW) linear_small_bwd_w_kernel<<<N, 128, 0, ST(stream)>>>(x, dy, dW, db, m, N, K);
-  if (dx) linear_small_bwd_x_kernel<<<(K + 127) / 128, 128, 0, ST(stream)>>>(W, dy, dx_add, dx, m, N, K);
+  if (dx) linear_small_bwd_x_kernel<<<dim3((K + 31) / 32, m), dim3(32, 8), 0, ST(stream)>>>(W, dy, dx_add, dx, m, N, K);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

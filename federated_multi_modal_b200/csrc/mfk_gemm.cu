@@ -8,7 +8,10 @@
 // `@ proj` / `@ text_projection` (clip/model.py:569-570, trainers/maple.py:76).
 //
 // Design: persistent, warp-specialised. warp0 = TMA producer (one thread), warp1 = tcgen05.mma issuer
-// (one thread), warp2 = TMEM allocator, warps4-7 = epilogue (one TMEM lane == one output row per thread).
+// (one thread), warp2 = TMEM allocator, warps4-11 = epilogue (one TMEM lane == one output row per thread; two
+// warps per lane quarter split the columns). Epilogue inputs (bias / residual / QuickGELU aux) are fetched while
+// the accumulator is still in flight; outputs are staged per warp in swizzled smem and written with TMA stores
+// (coalesced, M/N tails clipped by the tensor map).
 // smem ring of kStages x {A 128x64, B BNx64} bf16 tiles in 128-byte swizzle, filled by TMA and consumed
 // straight by UMMA descriptors; two 256-column TMEM accumulators so the epilogue of tile i overlaps the
 // MMAs of tile i+1. The last partial wave of tiles is split into narrower tiles (runtime UMMA N) so the
@@ -24,7 +27,9 @@ constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
 constexpr int UK = 16;        // UMMA K for 16-bit inputs
 constexpr int BOXN = 64;      // B rows per TMA box (tiles are 64/128/256 wide)
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kStageBufBytes = 4096;  // per epilogue warp: 32 rows x 128 B
 constexpr int kTmemCols = 512;
 
 struct GemmParams {
@@ -66,14 +71,16 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0,
 template <int BN, int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
+                    const __grid_constant__ CUtensorMap tmPre, const GemmParams p) {
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* stage_out = smem + kStages * kStageBytes;  // kEpiWarps x 4 KB output staging (1024-B aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + kEpiWarps * kStageBufBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
@@ -86,6 +93,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.out32) tma_prefetch_desc(&tmO32);
+    if (p.out16) tma_prefetch_desc(&tmO16);
+    if (p.outpre) tma_prefetch_desc(&tmPre);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -94,7 +104,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -165,84 +175,142 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which interleaved set of 32-column chunks
+    uint8_t* sbuf = stage_out + (warp - 4) * kStageBufBytes;
+    const uint32_t sbuf_u32 = smem_u32(sbuf);
+    // swizzled 16-byte chunk offsets of this lane's row inside the staging buffer
+    const uint32_t row128 = sbuf_u32 + lane * 128, x128 = lane & 7;            // 128-B rows, SWIZZLE_128B
+    const uint32_t row64a = sbuf_u32 + lane * 64, x64 = (lane >> 1) & 3;       // 64-B rows,  SWIZZLE_64B
+    const uint32_t row64b = row64a + 2048;                                     // second bf16 output
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int m0, n0, w;
       decode_tile(p, t, m0, n0, w);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      for (int c = 0; c < w; c += 32) {
+      bool waited = false;
+      for (int c = half * 32; c < w; c += 64) {
+        const int col = n0 + c;
+        const bool ok = row_ok && col < p.N;
+        // ---- operands that do not depend on the accumulator: issue their loads first
+        float4 bv[8];
+        float4 rv[8];
+        uint4 av[4];
+        if (p.bias && col < p.N) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
+        }
+        if (p.res && ok) {
+          const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)row * p.ldres + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rv[j] = r4[j];
+        }
+        if (p.act == 2 && ok) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) av[j] = __ldg(a4 + j);
+        }
+        if (!waited) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tc_wait_ld();
-        const int col = n0 + c;
-        if (row_ok && col < p.N) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b = __ldg(b4 + j);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
           }
-          if (p.act == 1) {
-            if (p.outpre) {
-              uint4* o = reinterpret_cast<uint4*>(p.outpre + (size_t)row * p.ldpre + col);
+        }
+        // previous TMA stores of this warp must have finished READING the staging buffer
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (p.act == 1) {
+          if (p.outpre) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            }
-            // the activation is applied to the bf16-rounded pre-activation that backward will re-read
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row64b + ((j ^ x64) << 4)),
+                           "r"(pack_bf16(v[8 * j], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                           "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+                           : "memory");
+          }
+          // the activation is applied to the bf16-rounded pre-activation that backward will re-read
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = quickgelu(__bfloat162float(__float2bfloat16_rn(v[j])));
-          } else if (p.act == 2) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
+          for (int j = 0; j < 32; ++j) v[j] = quickgelu(__bfloat162float(__float2bfloat16_rn(v[j])));
+        } else if (p.act == 2) {
+          if (ok) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 a = __ldg(a4 + j);
-              float2 u0 = unpack_bf16(a.x), u1 = unpack_bf16(a.y), u2 = unpack_bf16(a.z), u3 = unpack_bf16(a.w);
+              float2 u0 = unpack_bf16(av[j].x), u1 = unpack_bf16(av[j].y), u2 = unpack_bf16(av[j].z),
+                     u3 = unpack_bf16(av[j].w);
               v[8 * j] *= dquickgelu(u0.x); v[8 * j + 1] *= dquickgelu(u0.y);
               v[8 * j + 2] *= dquickgelu(u1.x); v[8 * j + 3] *= dquickgelu(u1.y);
               v[8 * j + 4] *= dquickgelu(u2.x); v[8 * j + 5] *= dquickgelu(u2.y);
               v[8 * j + 6] *= dquickgelu(u3.x); v[8 * j + 7] *= dquickgelu(u3.y);
             }
           }
-          if (p.res) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)row * p.ldres + col);
+        }
+        if (p.res && ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x = r4[j];
-              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-            }
-          }
-          if (p.out32) {
-            float4* o = reinterpret_cast<float4*>(p.out32 + (size_t)row * p.ld32 + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out16) {
-            uint4* o = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w;
           }
         }
+        const bool has_pre = p.act == 1 && p.outpre != nullptr;
+        if (p.out16 || has_pre) {
+          if (p.out16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row64a + ((j ^ x64) << 4)),
+                           "r"(pack_bf16(v[8 * j], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                           "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+                           : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out16) tma_store_2d(&tmO16, sbuf, col, m0 + q * 32);
+            if (has_pre) tma_store_2d(&tmPre, sbuf + 2048, col, m0 + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (p.out32) {
+          if (p.out16 || has_pre) {  // the fp32 image needs the whole buffer: wait for the bf16 stores to drain it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row128 + ((j ^ x128) << 4)), "f"(v[4 * j]),
+                         "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                         : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO32, sbuf, col, m0 + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      if (!waited) {  // narrow tile: this warp had no chunk, but it still takes part in the hand-shake
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output stores complete before exit
   }
 
   tc_fence_before();
@@ -255,7 +323,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, int kStages>
 constexpr size_t gemm_smem_bytes() {
-  return (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + (2 * kStages + 4) * 8 + 16 + 1024;
+  return (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + kEpiWarps * kStageBufBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 }
 
 int g_num_sms = 0;
@@ -293,6 +361,22 @@ int mfk_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uin
   return r == CUDA_SUCCESS ? MFK_OK : MFK_EDRIVER;
 }
 
+int mfk_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                     uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+  int rc = load_encode();
+  if (rc != MFK_OK) return rc;
+  if (!mfk_aligned16(base) || (ld_elems * elem_bytes) % 16 != 0) return MFK_EALIGN;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MFK_OK : MFK_EDRIVER;
+}
+
 static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -304,7 +388,8 @@ static int num_sms() {
 }
 
 template <int BN, int kStages>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO32,
+                       const CUtensorMap& tmO16, const CUtensorMap& tmPre, const GemmParams& p, int grid,
                        cudaStream_t st) {
   static bool configured = false;
   constexpr size_t smem = gemm_smem_bytes<BN, kStages>();
@@ -314,7 +399,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  gemm_bf16_tn_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  gemm_bf16_tn_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(tmA, tmB, tmO32, tmO16, tmPre, p);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -362,8 +447,17 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
   if (rc != MFK_OK) return rc;
   rc = mfk_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BOXN, BK);
   if (rc != MFK_OK) return rc;
+  // output tensor maps: 32-row x 32-column boxes (one epilogue warp's chunk); absent outputs get a dummy map
+  CUtensorMap tmO32 = tmA, tmO16 = tmA, tmPre = tmA;
+  if (out_f32 && (rc = mfk_make_tmap_2d(&tmO32, out_f32, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ld32, 32, 32, 128)))
+    return rc;
+  if (out_bf16 && (rc = mfk_make_tmap_2d(&tmO16, out_bf16, 2, (uint64_t)M, (uint64_t)N, (uint64_t)ld16, 32, 32, 64)))
+    return rc;
+  if (out_pre_bf16 &&
+      (rc = mfk_make_tmap_2d(&tmPre, out_pre_bf16, 2, (uint64_t)M, (uint64_t)N, (uint64_t)ldpre, 32, 32, 64)))
+    return rc;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, p, grid, st);
-  return launch_gemm<128, 6>(tmA, tmB, p, grid, st);
+  if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+  return launch_gemm<128, 6>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
 }

@@ -400,6 +400,44 @@ class MapleEngine:
     def last_image_features(self) -> torch.Tensor:
         return self._bufs["vis.feat"].view(-1)[: self.vis.N * self.E].view(self.vis.N, self.E).clone()
 
+    def _side_stream(self):
+        st = self._bufs.get("__side_stream__")
+        if st is None:
+            st = torch.cuda.Stream(device=self.dev)
+            self._bufs["__side_stream__"] = st
+        return st
+
+    def _tower_bwd(self, tw: _Tower, dfeat, proj, xs, stat, rows, lnname, R, deep_row0):
+        """Backward of one tower from d(features) down to the gradient at its (post-embedding) input, which is
+        left in tw.ws["g"]. Returns {deep prompt index: gradient [n_ctx, D]}."""
+        p, G, n, nd = self.p, self.g, self.n, self.J - 1
+        ln_grads = self.trainable == "reference"
+        ws, D = tw.ws, tw.D
+        d16 = self._buf(tw.name + ".dfeat16", (R, self.E), BF16)
+        ops.cast_bf16(dfeat, d16)
+        dy = self._buf(tw.name + ".dy", (R, D), F32)
+        ops.gemm(d16, proj, out_f32=dy)
+        dxr = self._buf(tw.name + ".dxr", (R, D), F32)
+        ops.layernorm_bwd(dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=dxr,
+                          dgamma=G[lnname + ".weight"] if ln_grads else None,
+                          dbeta=G[lnname + ".bias"] if ln_grads else None, partial_ws=ws["lnp"], M=R)
+        ws["g"].zero_()
+        ws["g16"].zero_()
+        ops.scatter_rows(dxr, rows, ws["g"], ws["g16"])
+        got = {}
+        for l in reversed(range(tw.L)):
+            self._block_bwd(tw, l)
+            if l >= 1 and (l - 1) < nd:
+                dp = self._buf(f"{tw.name}.dprompt{l - 1}", (n, D), F32)
+                ops.prompt_splice_bwd(ws["g"], ws["g16"], dp, tw.N, tw.T, deep_row0, n, True, True)
+                got[l - 1] = dp
+        for i in range(nd):  # deep prompts beyond the tower depth are never spliced: zero gradient
+            if i not in got:
+                z = self._buf(f"{tw.name}.dprompt{i}", (n, D), F32)
+                z.zero_()
+                got[i] = z
+        return got
+
     # ------------------------------------------------------------------ public: training step
     @torch.no_grad()
     def forward_backward(self, img: torch.Tensor, label: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
@@ -409,9 +447,17 @@ class MapleEngine:
         B, C, n, nd = img.shape[0], self.C, self.n, self.J - 1
         p, G = self.p, self.g
         self._text_cache_valid = False
+        # The two towers are independent until the logits head: the (small) text tower runs on a side stream so
+        # its latency-bound kernels fill the gaps of the vision tower; inside a CUDA graph this becomes two
+        # parallel branches.
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
         self._prompt_learner_fwd()
-        ft, txs, tstat = self._text_features(True)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ft, txs, tstat = self._text_features(True)
         fi, vxs, vstat = self._image_features(img, True)
+        main.wait_stream(side)
         logits = self._buf("head.logits", (B, C), F32)
         loss = loss_out if loss_out is not None else self._buf("head.loss", (1,), F32)
         dfi, dft = self._buf("head.dfi", (B, self.E), F32), self._buf("head.dft", (C, self.E), F32)
@@ -419,44 +465,23 @@ class MapleEngine:
         ops.head_forward_backward(fi, ft, self.logit_scale, label, logits, loss, dfi, dft, hws)
         ln_grads = self.trainable == "reference"
 
-        d_deep = {}
-        for tw, dfeat, proj, xs, stat, rows, lnname, R, deep_row0 in (
-                (self.vis, dfi, self.vproj, vxs, vstat, self.cls_rows, "image_encoder.ln_post", B, self.Tv - n),
-                (self.txt, dft, self.tproj, txs, tstat, self.eot_rows, "text_encoder.ln_final", C, 1)):
-            ws, D = tw.ws, tw.D
-            d16 = self._buf(tw.name + ".dfeat16", (R, self.E), BF16)
-            ops.cast_bf16(dfeat, d16)
-            dy = self._buf(tw.name + ".dy", (R, D), F32)
-            ops.gemm(d16, proj, out_f32=dy)
-            dxr = self._buf(tw.name + ".dxr", (R, D), F32)
-            ops.layernorm_bwd(dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=dxr,
-                              dgamma=G[lnname + ".weight"] if ln_grads else None,
-                              dbeta=G[lnname + ".bias"] if ln_grads else None, partial_ws=ws["lnp"], M=R)
-            ws["g"].zero_()
-            ws["g16"].zero_()
-            ops.scatter_rows(dxr, rows, ws["g"], ws["g16"])
-            dd = []
-            for l in reversed(range(tw.L)):
-                self._block_bwd(tw, l)
-                if l >= 1 and (l - 1) < nd:
-                    dp = self._buf(f"{tw.name}.dprompt{l - 1}", (n, D), F32)
-                    ops.prompt_splice_bwd(ws["g"], ws["g16"], dp, tw.N, tw.T, deep_row0, n, True, True)
-                    dd.append((l - 1, dp))
-            d_deep[tw.name] = dict(dd)
-
-        # ---- tower inputs
-        vws, tws = self.vis.ws, self.txt.ws
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dt = self._tower_bwd(self.txt, dft, self.tproj, txs, tstat, self.eot_rows, "text_encoder.ln_final", C, 1)
+            d_ctx_t = self._buf("pl.dctx_t", (n, self.txt.D), F32)
+            ops.prompt_splice_bwd(self.txt.ws["g"], None, d_ctx_t, C, self.Te, 1, n, False, False)
+        dv = self._tower_bwd(self.vis, dfi, self.vproj, vxs, vstat, self.cls_rows, "image_encoder.ln_post", B,
+                             self.Tv - n)
+        vws = self.vis.ws
         ops.layernorm_bwd(vws["g"], self.vx0, self.vstat0[0], self.vstat0[1], p["image_encoder.ln_pre.weight"],
                           g_out=vws["g"], dgamma=G["image_encoder.ln_pre.weight"] if ln_grads else None,
                           dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None, partial_ws=vws["lnp"])
         d_shared = self._buf("pl.dshared", (n, self.vis.D), F32)
         ops.prompt_splice_bwd(vws["g"], None, d_shared, B, self.Tv, self.Tv - n, n, True, False)
-        d_ctx_t = self._buf("pl.dctx_t", (n, self.txt.D), F32)
-        ops.prompt_splice_bwd(tws["g"], None, d_ctx_t, C, self.Te, 1, n, False, False)
+        main.wait_stream(side)
 
         # ---- prompt learner backward
         pl = "prompt_learner."
-        dv, dt = d_deep[self.vis.name], d_deep[self.txt.name]
         for i in range(nd):
             Wn = f"{pl}compound_prompt_projections.{i}"
             if i % 2 == 0:

@@ -43,7 +43,7 @@ def attn_fwd(qkv, out, lse, N, T, heads, causal):
 
 
 def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal):
-    call("mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, int(causal), stream_ptr())
+    call("mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, int(causal), stream_ptr(), kernels=3)
 
 
 def layernorm_fwd(x, gamma, beta, *, rowidx=None, y_bf16=None, y_f32=None, x_save=None, mean=None, rstd=None,
@@ -63,12 +63,13 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, g_in=None, g_out, g_out_bf16=None
     D = x.shape[-1]
     M = x.numel() // D if M is None else M
     call("mfk_layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma,
-         dbeta, partial_ws, int(accumulate), M, D, stream_ptr())
+         dbeta, partial_ws, int(accumulate), M, D, stream_ptr(),
+         kernels=1 + (dgamma is not None or dbeta is not None))
 
 
 def colsum(x, out, partial_ws, accumulate=False):
     call("mfk_colsum", x, int(x.dtype == BF16), x.stride(0), x.shape[0], x.shape[1], out, partial_ws,
-         int(accumulate), stream_ptr())
+         int(accumulate), stream_ptr(), kernels=2)
 
 
 def patch_im2col(img, out):
@@ -113,7 +114,8 @@ def linear_small_fwd(x, W, b, y):
 
 
 def linear_small_bwd(x, W, dy, *, dW=None, db=None, dx_add=None, dx=None):
-    call("mfk_linear_small_bwd", x, W, dy, dW, db, dx_add, dx, x.shape[0], W.shape[0], W.shape[1], stream_ptr())
+    call("mfk_linear_small_bwd", x, W, dy, dW, db, dx_add, dx, x.shape[0], W.shape[0], W.shape[1], stream_ptr(),
+         kernels=(dW is not None) + (dx is not None))
 
 
 def head_workspace_floats(B, C, E) -> int:
@@ -124,7 +126,7 @@ def head_forward_backward(img_feat, txt_feat, logit_scale, label, logits, loss, 
     B, E = img_feat.shape
     C = txt_feat.shape[0]
     call("mfk_head_forward_backward", img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws, B, C, E,
-         stream_ptr())
+         stream_ptr(), kernels=2 if label is None else 6)
 
 
 def fedavg_reduce(ptrs_dev, weights_dev, divisor, K, n, in_is_fp16, out_f32, out_f16, flags_dev):
@@ -138,7 +140,7 @@ def check_finite(t, flag_dev):
 
 
 def grad_norm(g, partial_ws, norm_out):
-    call("mfk_grad_norm", g, g.numel(), partial_ws, norm_out, stream_ptr())
+    call("mfk_grad_norm", g, g.numel(), partial_ws, norm_out, stream_ptr(), kernels=2)
 
 
 def sgd_step(p, g, mom, hyper_dev, total_norm_dev, n=None):

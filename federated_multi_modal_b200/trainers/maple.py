@@ -369,16 +369,11 @@ class MaPLe(TrainerX):
         norm = eng.sgd_step(0.0, hyper=self._hyper_dev)
         self._readback[1:2].copy_(norm)
 
-    def forward_backward(self, batch):
-        """fwd + bwd + clip_grad_norm_(1.0) + SGD step (trainers/maple.py:547-627) with a single host sync."""
-        image, label, caption = self.parse_batch_train(batch)
-        if caption is not None and isinstance(caption, list) and any(c is not None for c in caption):
-            raise NotImplementedError("caption branch is out of scope (SURVEY.md §2 #11)")
-        self.total_batches += 1
+    def step_async(self, image, label):
+        """Enqueue one training step (fwd + bwd + clip + SGD) for device-resident inputs WITHOUT any host
+        synchronisation; loss / grad-norm / validity land in device buffers read by ``read_step_result``."""
         model, eng = self.model, self.model.engine
         model._sync_to_engine()
-        image = image.to(F32).contiguous()
-        label = label.to(torch.int64).contiguous()
         B = image.shape[0]
         if getattr(self, "_readback", None) is None:
             self._readback = torch.zeros(2, device=self.device, dtype=F32)
@@ -391,17 +386,16 @@ class MaPLe(TrainerX):
                 self._static_lab = torch.empty_like(label)
                 self._static_img.copy_(image); self._static_lab.copy_(label)
                 # warm-up outside capture (lazy driver entry points, workspace allocation, smem attributes);
-                # parameters / momentum are restored afterwards so the warm-up is not a training step
+                # parameters / momentum are restored afterwards so warm-up and capture are not training steps
                 snap = (eng.params.clone(), eng.momentum.clone(), eng.mom_initialized)
                 self._step_kernels(self._static_img, self._static_lab)
-                eng.params.copy_(snap[0]); eng.momentum.copy_(snap[1]); eng.mom_initialized = snap[2]
-                eng.repack_trainable()
                 torch.cuda.synchronize()
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._step_kernels(self._static_img, self._static_lab)
                 eng.params.copy_(snap[0]); eng.momentum.copy_(snap[1]); eng.mom_initialized = snap[2]
                 eng.repack_trainable()
+                self._flag.zero_()
                 self._graph_B = B
                 self._graph_gen = eng.buffer_generation
                 self._hyper_vals = None
@@ -413,14 +407,28 @@ class MaPLe(TrainerX):
         else:
             self._step_kernels(image, label)
         model._arena_newer = True
-        # one D2H read: loss, pre-clip grad norm, input validity flag
+
+    def read_step_result(self):
+        """One D2H read + stream sync: (loss, pre-clip grad norm, input validity flag)."""
         self._host[0:2].copy_(self._readback, non_blocking=True)
-        flag = self._flag.to("cpu", non_blocking=False)  # synchronises the stream
-        self._flag.zero_()
-        loss, norm = float(self._host[0]), float(self._host[1])
-        if int(flag) & 1:
+        flag = int(self._flag.to("cpu"))  # synchronises the stream
+        if flag:
+            self._flag.zero_()
+        return float(self._host[0]), float(self._host[1]), flag
+
+    def forward_backward(self, batch):
+        """fwd + bwd + clip_grad_norm_(1.0) + SGD step (trainers/maple.py:547-627) with a single host sync."""
+        image, label, caption = self.parse_batch_train(batch)
+        if caption is not None and isinstance(caption, list) and any(c is not None for c in caption):
+            raise NotImplementedError("caption branch is out of scope (SURVEY.md §2 #11)")
+        self.total_batches += 1
+        image = image.to(F32).contiguous()
+        label = label.to(torch.int64).contiguous()
+        self.step_async(image, label)
+        loss, norm, flag = self.read_step_result()
+        if flag & 1:
             raise ValueError("NaN values in input image")  # trainers/maple.py:532-535
-        if int(flag) & 2:
+        if flag & 2:
             raise ValueError("Inf values in input image")
         if not math.isfinite(loss):
             raise RuntimeError("NaN/Inf in total loss")

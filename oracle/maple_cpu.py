@@ -356,6 +356,9 @@ class MapleOracle:
                 dx[:, 1:1 + n, :] = 0
         d_ctx = dx[:, 1:1 + n, :].sum(0)
 
+        # deep prompts beyond the tower depth are never spliced: zero gradient
+        d_deep_vis = [torch.zeros_like(deep_vis[i]) if d is None else d for i, d in enumerate(d_deep_vis)]
+        d_deep_text = [torch.zeros_like(deep_text[i]) if d is None else d for i, d in enumerate(d_deep_text)]
         # ---------------- prompt learner backward
         pl = "prompt_learner."
         for i in range(nd):
