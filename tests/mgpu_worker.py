@@ -1,0 +1,83 @@
+"""Worker for multi-rank tests (launched by torchrun, nccl on GPUs or gloo on CPU).
+Checks FedAvgExchange: gather order, validity handling, and (CUDA) bit-exact reduction vs the oracle."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from federated_multi_modal_b200.fed import FedAvgExchange, clients_of_rank  # noqa: E402
+from oracle.maple_cpu import fedavg_oracle  # noqa: E402
+
+
+def client_tensor(k, n):
+    g = torch.Generator().manual_seed(1000 + k)
+    return torch.randn(n, generator=g)
+
+
+def main():
+    backend = sys.argv[1]
+    transport = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo")
+    n, k_local = 4096 * 3 + 64, 2
+    K = k_local * world
+    mine = clients_of_rank(K, rank, world)
+    assert mine == list(range(rank * k_local, (rank + 1) * k_local))
+    ex = FedAvgExchange(n, k_local, dev, transport=transport)
+    for rnd in range(2):
+        for j, k in enumerate(mine):
+            t = client_tensor(k + 100 * rnd, n)
+            ok = True
+            if rnd == 1 and k == 1:
+                t[5] = float("nan")          # invalid weights -> must be excluded everywhere
+            if rnd == 1 and k == K - 1:
+                ok = False                    # failed local training
+            ex.publish(j, t.to(dev), ok=ok, n_samples=10 + k)
+        rows = ex.gather()
+        assert len(rows) == K
+        for k in range(K):                    # rank-major gather order == client order
+            want = client_tensor(k + 100 * rnd, n)
+            got = rows[k].cpu()
+            if rnd == 1 and k == 1:
+                assert torch.isnan(got[5])
+                got = got.clone(); got[5] = 0.0; want[5] = 0.0
+            assert torch.equal(got, want), (rank, rnd, k)
+        status = ex.status.cpu()
+        assert [float(s) for s in status[:, 1]] == [10.0 + k for k in range(K)]
+        if backend == "nccl":
+            for weighted in (False, True):
+                m32, m16, valid, bad = ex.reduce(rows, weighted=weighted)
+                expect_valid = [k for k in range(K) if not (rnd == 1 and k in (1, K - 1))]
+                assert valid == expect_valid, (valid, expect_valid)
+                ref_rows = [client_tensor(k + 100 * rnd, n) for k in expect_valid]
+                w = [10.0 + k for k in expect_valid] if weighted else None
+                r32, r16 = fedavg_oracle(ref_rows, w)
+                assert torch.equal(m32.cpu(), r32), (rank, rnd, weighted)
+                assert torch.equal(m16.cpu(), r16)
+                # identical on every rank
+                chk = m32.double().sum().reshape(1).clone()
+                lst = [torch.zeros_like(chk) for _ in range(world)]
+                dist.all_gather(lst, chk)
+                assert all(torch.equal(x, lst[0]) for x in lst)
+        else:
+            ex.status.cpu()
+        dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK backend={backend} world={world} transport={ex.transport}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

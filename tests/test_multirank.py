@@ -1,0 +1,41 @@
+"""Multi-rank host logic: world_size-2 gloo on CPU (always), nccl + NVLink p2p on >= 2 GPUs (gpu marker)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _torchrun(nproc, *args, port=29533):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), *args]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+
+
+def test_fedavg_exchange_gloo_world2():
+    r = _torchrun(2, "gloo", "nccl", port=29541)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_client_assignment():
+    from federated_multi_modal_b200.fed import clients_of_rank
+    assert [clients_of_rank(32, r, 8) for r in (0, 7)] == [[0, 1, 2, 3], [28, 29, 30, 31]]
+    assert sorted(sum((clients_of_rank(8, r, 2) for r in range(2)), [])) == list(range(8))
+    with pytest.raises(ValueError):
+        clients_of_rank(10, 0, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_fedavg_exchange_nccl(transport):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = _torchrun(min(n, 8), "nccl", transport, port=29551 if transport == "p2p" else 29552)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    if transport == "p2p":
+        assert "transport=p2p" in r.stdout, r.stdout[-2000:]
