@@ -21,8 +21,11 @@ SIGNATURES = {
     "mfk_version": [],
     "mfk_error_string": [I],
     "mfk_gemm_bf16": [P, L, P, L, I, I, I, P, I, P, L, P, L, P, L, P, L, P, L, I, P],
+    "mfk_gemm_bf16_at_b": [P, L, P, L, I, I, I, P, L, P],
     "mfk_attn_fwd": [P, P, P, I, I, I, I, P],
+    "mfk_attn_fwd_tc": [P, P, P, I, I, I, I, P],
     "mfk_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P],
+    "mfk_attn_bwd_tc": [P, P, P, P, P, P, I, I, I, I, P],
     "mfk_layernorm_fwd": [P, P, P, P, P, P, P, P, P, I, I, F, P],
     "mfk_ln_bwd_ctas": [I],
     "mfk_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, I, I, I, P],

@@ -404,3 +404,597 @@ extern "C" int mfk_attn_bwd(const void* qkv, const void* out, const void* d_out,
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
+
+// =====================================================================================================
+// tcgen05 / TMEM / TMA flash attention FORWARD (T <= 256: the whole key range of a sequence is one UMMA N tile).
+//   S = Q K^T   : tcgen05.mma  M=128 (queries) x N=Tk (keys, multiple of 16) x K=64, A/B K-major from TMA tiles
+//   P = softmax : 4 warps, one TMEM lane (= query row) per thread, two passes over S in TMEM (max, then exp2/sum),
+//                 P written as bf16 into 128B-swizzled smem in the K-major A-operand layout
+//   O = P V     : tcgen05.mma  M=128 x N=64 x K=Tk, B = V tile used as an MN-major operand (no transpose)
+// Persistent CTAs; Q/K/V smem and the S/O TMEM accumulator are double-buffered so the TMA loads and the
+// QK^T MMA of work item i+1 overlap the softmax of item i (the kernel is MUFU/issue bound, not tensor bound).
+namespace {
+using namespace mfk;
+
+constexpr int TC_SOFTMAX_WARPS = 8;  // two warps per TMEM lane quarter, each takes alternate 32-column chunks
+constexpr int TC_THREADS = (TC_SOFTMAX_WARPS + 1) * 32;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// named barrier shared by the two warps that own the same TMEM lane quarter
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+struct AttnTcParams {
+  const bf16* qkv;
+  bf16* out;
+  float* lse;
+  int T, Tk, heads, m_tiles, total_items;
+  float c1;  // softmax scale * log2(e)
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  const int Tk = p.Tk, D = p.heads * HD;
+  const uint32_t kvBytes = (uint32_t)Tk * 128u;
+  const int nkb = (Tk + 63) / 64;  // 64-key column blocks of P
+  uint8_t* sQ = smem;                       // [2][128 x 128 B]
+  uint8_t* sK = sQ + 2 * 16384;             // [2][Tk x 128 B]
+  uint8_t* sV = sK + 2 * kvBytes;           // [2][Tk x 128 B]
+  uint8_t* sP = sV + 2 * kvBytes;           // [nkb][128 x 128 B]
+  float* sx = reinterpret_cast<float*>(sP + (size_t)nkb * 16384);  // [2 halves][128 rows] max / sum exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 256);
+  uint64_t* qkv_full = bars;        // [2]
+  uint64_t* s_full = bars + 2;      // [2]
+  uint64_t* o_full = bars + 4;      // [2]
+  uint64_t* tmem_free = bars + 6;   // [2]
+  uint64_t* p_full = bars + 8;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == TC_SOFTMAX_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&qkv_full[b], 1);
+        mbar_init(&s_full[b], 1);
+        mbar_init(&o_full[b], 1);
+        mbar_init(&tmem_free[b], TC_SOFTMAX_WARPS);
+      }
+      mbar_init(p_full, TC_SOFTMAX_WARPS);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto item_coords = [&](int i, int& n, int& h, int& mt) {
+    const int w = (int)blockIdx.x + i * (int)gridDim.x;
+    mt = w % p.m_tiles;
+    h = (w / p.m_tiles) % p.heads;
+    n = w / (p.m_tiles * p.heads);
+  };
+
+  if (warp == TC_SOFTMAX_WARPS) {
+    // ============================ control: TMA loads + MMA issue (one thread) ============================
+    if (lane == 0) {
+      auto issue_loads = [&](int i) {
+        int n, h, mt;
+        item_coords(i, n, h, mt);
+        const int b = i & 1;
+        mbar_arrive_expect_tx(&qkv_full[b], 16384u + 2u * kvBytes);
+        tma_load_2d(&tmQ, &qkv_full[b], sQ + b * 16384, h * HD, n * p.T + mt * 128);
+        tma_load_2d(&tmKV, &qkv_full[b], sK + b * kvBytes, D + h * HD, n * p.T);
+        tma_load_2d(&tmKV, &qkv_full[b], sV + b * kvBytes, 2 * D + h * HD, n * p.T);
+      };
+      auto issue_s = [&](int i) {
+        const int b = i & 1;
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        mbar_wait(&qkv_full[b], par);
+        mbar_wait(&tmem_free[b], par ^ 1u);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, Tk, 0, 0);
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ + b * 16384));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK + b * kvBytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc + 2ull * k, bdesc + 2ull * k, idesc, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+      };
+      if (n_items > 0) issue_loads(0);
+      if (n_items > 1) issue_loads(1);
+      if (n_items > 0) issue_s(0);
+      for (int i = 0; i < n_items; ++i) {
+        const int b = i & 1;
+        if (i + 1 < n_items) issue_s(i + 1);
+        mbar_wait(p_full, (uint32_t)i & 1u);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
+        const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV + b * kvBytes);
+        const int ksteps = Tk / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t adesc = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+          const uint64_t bdesc = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
+          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[b]);
+        if (i + 2 < n_items) {
+          mbar_wait(&o_full[b], (uint32_t)(i >> 1) & 1u);  // Q/K/V buffer b (and P) no longer read
+          issue_loads(i + 2);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ softmax + epilogue warps ============================
+    const int q = warp & 3, half = warp >> 2;
+    const int rl = q * 32 + lane;  // row inside the 128-row tile == TMEM lane
+    const uint32_t prow = smem_u32(sP) + (uint32_t)rl * 128u;
+    const uint32_t x7 = (uint32_t)rl & 7u;
+    for (int i = 0; i < n_items; ++i) {
+      int n, h, mt;
+      item_coords(i, n, h, mt);
+      const int b = i & 1;
+      const uint32_t par = (uint32_t)(i >> 1) & 1u;
+      const int row = mt * 128 + rl;  // query index inside the sequence
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * 256u;
+      const int kmax = CAUSAL ? min(p.T, row + 1) : p.T;  // keys [0, kmax) are visible
+      mbar_wait(&s_full[b], par);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int c = half * 32; c < Tk; c += 64) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tc_wait_ld();
+        if (!CAUSAL && c + 32 <= p.T) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < kmax) ? __uint_as_float(r[j]) : -INFINITY);
+        }
+      }
+      sx[half * 128 + rl] = mx;
+      pair_sync(q);
+      mx = fmaxf(mx, sx[(half ^ 1) * 128 + rl]);
+      const float mc = (mx == -INFINITY) ? 0.f : mx * p.c1;
+      float l = 0.f;
+      for (int c = half * 32; c < Tk; c += 64) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tc_wait_ld();
+        float pv[32];
+        if (!CAUSAL && c + 32 <= p.T) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = fast_exp2(__uint_as_float(r[j]) * p.c1 - mc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            pv[j] = (c + j < kmax) ? fast_exp2(__uint_as_float(r[j]) * p.c1 - mc) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) l += pv[j];
+        const uint32_t blk = prow + (uint32_t)(c >> 6) * 16384u;
+        const uint32_t ch0 = (uint32_t)(c & 63) >> 3;  // first 16-byte chunk of this 32-column group: 0 or 4
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((ch0 + j) ^ x7) << 4)),
+                       "r"(pack_bf16(pv[8 * j], pv[8 * j + 1])), "r"(pack_bf16(pv[8 * j + 2], pv[8 * j + 3])),
+                       "r"(pack_bf16(pv[8 * j + 4], pv[8 * j + 5])), "r"(pack_bf16(pv[8 * j + 6], pv[8 * j + 7]))
+                       : "memory");
+      }
+      pair_sync(q);                       // both warps have read the partner's max: the slot can be reused
+      sx[half * 128 + rl] = l;
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      pair_sync(q);
+      l += sx[(half ^ 1) * 128 + rl];
+      // ---- epilogue: O = (P V) / l ; each warp of the pair writes 32 of the 64 head-dim columns
+      mbar_wait(&o_full[b], par);
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = p.out + ((size_t)n * p.T + row) * D + h * HD;
+      {
+        const int c = half * 32;
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tc_wait_ld();
+        if (row < p.T) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c + 8 * j) = v;
+          }
+        }
+      }
+      if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[b]);
+      pair_sync(q);  // the partner has consumed this warp's partial sum before the next item overwrites it
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_SOFTMAX_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int g_attn_sms = 0;
+}  // namespace
+
+extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int heads, int causal,
+                               void* stream) {
+  if (!qkv || !out || N <= 0 || T <= 0 || T > 256 || heads <= 0) return MFK_EARG;
+  if (g_attn_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_attn_sms <= 0) g_attn_sms = 148;
+  }
+  const int D = heads * HD;
+  AttnTcParams p;
+  p.qkv = static_cast<const bf16*>(qkv);
+  p.out = static_cast<bf16*>(out);
+  p.lse = lse;
+  p.T = T;
+  p.Tk = (T + 15) / 16 * 16;
+  p.heads = heads;
+  p.m_tiles = (T + 127) / 128;
+  p.total_items = N * heads * p.m_tiles;
+  p.c1 = 0.125f * kLog2e;
+  CUtensorMap tmQ, tmKV;
+  int rc = mfk_make_tmap_2d(&tmQ, qkv, 2, (uint64_t)N * T, (uint64_t)3 * D, (uint64_t)3 * D, 128, 64, 128);
+  if (rc != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmKV, qkv, 2, (uint64_t)N * T, (uint64_t)3 * D, (uint64_t)3 * D, (uint32_t)p.Tk, 64,
+                             128)) != MFK_OK)
+    return rc;
+  const int nkb = (p.Tk + 63) / 64;
+  const size_t smem = 2 * 16384 + 4 * (size_t)p.Tk * 128 + (size_t)nkb * 16384 + 1024 + 128 + 1024;
+  const int grid = p.total_items < g_attn_sms ? p.total_items : g_attn_sms;
+  cudaError_t e;
+  if (causal) {
+    e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+  } else {
+    e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+  }
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+// =====================================================================================================
+// tcgen05 / TMEM / TMA flash attention BACKWARD (T <= 256), two deterministic kernels (no atomics):
+//   dq kernel,  item = (sequence, head, 128-query tile):   S = Q_i K^T, dP = dO_i V^T  ->  dS  ->  dQ_i = dS K
+//   dkv kernel, item = (sequence, head, 128-key tile):      S^T = K_j Q^T, dP^T = V_j dO^T -> P^T, dS^T
+//                                                           dV_j = P^T dO,  dK_j = dS^T Q
+// One TMEM lane (= query row resp. key row) per thread for the elementwise part; P / dS are staged as bf16 in
+// 128B-swizzled smem in the K-major A-operand layout; K / Q / dO are re-used in place as MN-major B operands
+// (no transposed copies). The accumulators of the second GEMMs alias the TMEM columns of S / dP.
+namespace {
+using namespace mfk;
+
+struct AttnBwdTcParams {
+  const float* lse;
+  const float* delta;
+  bf16* dqkv;
+  int T, Tk, heads, m_tiles, total_items;
+  float c1, scale;
+};
+
+// MODE 0: dq kernel, MODE 1: dkv kernel
+template <int MODE, bool CAUSAL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // 128-row boxes of qkv (Q_i | K_j, V_j)
+                   const __grid_constant__ CUtensorMap tmFull,   // Tk-row boxes of qkv (K, V | Q)
+                   const __grid_constant__ CUtensorMap tmDoTile, // 128-row boxes of dO
+                   const __grid_constant__ CUtensorMap tmDoFull, // Tk-row boxes of dO
+                   const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw_tcb[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tcb) + 1023) & ~uintptr_t(1023));
+  const int Tk = p.Tk, D = p.heads * HD;
+  const uint32_t fullBytes = (uint32_t)Tk * 128u;
+  const int nkb = (Tk + 63) / 64;
+  // MODE 0: tA = Q_i, tB = dO_i, fA = K, fB = V, st0 = dS
+  // MODE 1: tA = K_j, tB = V_j,  fA = Q, fB = dO, st0 = P^T, st1 = dS^T
+  uint8_t* tA = smem;
+  uint8_t* tB = tA + 16384;
+  uint8_t* fA = tB + 16384;
+  uint8_t* fB = fA + fullBytes;
+  uint8_t* st0 = fB + fullBytes;
+  uint8_t* st1 = st0 + (size_t)nkb * 16384;
+  uint8_t* after = MODE == 1 ? st1 + (size_t)nkb * 16384 : st1;
+  float* sL = reinterpret_cast<float*>(after);  // [256] lse   (MODE 1)
+  float* sD = sL + 256;                         // [256] delta (MODE 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t* ld_full = bars;        // TMA loads landed
+  uint64_t* sd_full = bars + 1;    // S and dP accumulators complete
+  uint64_t* ds_full = bars + 2;    // staged bf16 operands written (count 4)
+  uint64_t* out_full = bars + 3;   // second GEMM(s) complete
+  uint64_t* item_free = bars + 4;  // epilogue finished with TMEM + smem (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == TC_SOFTMAX_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmTile);
+      tma_prefetch_desc(&tmFull);
+      tma_prefetch_desc(&tmDoTile);
+      tma_prefetch_desc(&tmDoFull);
+      mbar_init(ld_full, 1);
+      mbar_init(sd_full, 1);
+      mbar_init(ds_full, TC_SOFTMAX_WARPS);
+      mbar_init(out_full, 1);
+      mbar_init(item_free, TC_SOFTMAX_WARPS);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t colS = 0, colDP = 256;  // accumulators of the second GEMMs alias these
+
+  auto item_coords = [&](int i, int& n, int& h, int& mt) {
+    const int w = (int)blockIdx.x + i * (int)gridDim.x;
+    mt = w % p.m_tiles;
+    h = (w / p.m_tiles) % p.heads;
+    n = w / (p.m_tiles * p.heads);
+  };
+
+  if (warp == TC_SOFTMAX_WARPS) {
+    if (lane == 0) {
+      for (int i = 0; i < n_items; ++i) {
+        int n, h, mt;
+        item_coords(i, n, h, mt);
+        const uint32_t par = (uint32_t)i & 1u;
+        mbar_wait(item_free, par ^ 1u);  // previous item fully drained (passes for i = 0)
+        mbar_arrive_expect_tx(ld_full, 2u * 16384u + 2u * fullBytes);
+        const int row_t = n * p.T + mt * 128, row_f = n * p.T;
+        if (MODE == 0) {
+          tma_load_2d(&tmTile, ld_full, tA, h * HD, row_t);             // Q_i
+          tma_load_2d(&tmDoTile, ld_full, tB, h * HD, row_t);           // dO_i
+          tma_load_2d(&tmFull, ld_full, fA, D + h * HD, row_f);         // K
+          tma_load_2d(&tmFull, ld_full, fB, 2 * D + h * HD, row_f);     // V
+        } else {
+          tma_load_2d(&tmTile, ld_full, tA, D + h * HD, row_t);         // K_j
+          tma_load_2d(&tmTile, ld_full, tB, 2 * D + h * HD, row_t);     // V_j
+          tma_load_2d(&tmFull, ld_full, fA, h * HD, row_f);             // Q
+          tma_load_2d(&tmDoFull, ld_full, fB, h * HD, row_f);           // dO
+        }
+        mbar_wait(ld_full, par);
+        tc_fence_after();
+        {  // S (or S^T) and dP (or dP^T): M=128, N=Tk, K=64, all operands K-major
+          const uint32_t idesc = umma_idesc_bf16(128, Tk, 0, 0);
+          const uint64_t a0 = umma_desc_k_sw128(smem_u32(tA)), b0 = umma_desc_k_sw128(smem_u32(fA));
+          const uint64_t a1 = umma_desc_k_sw128(smem_u32(tB)), b1 = umma_desc_k_sw128(smem_u32(fB));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colS, a0 + 2ull * k, b0 + 2ull * k, idesc, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colDP, a1 + 2ull * k, b1 + 2ull * k, idesc, k > 0);
+          umma_commit(sd_full);
+        }
+        mbar_wait(ds_full, par);
+        tc_fence_after();
+        {  // second GEMM(s): M=128, N=64, K=Tk; A = staged bf16 (K-major), B = full tile as MN-major
+          const uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
+          const int ksteps = Tk / 16;
+          const uint32_t s0 = smem_u32(st0), s1 = smem_u32(st1);
+          const uint32_t bq = smem_u32(fA), bdo = smem_u32(fB);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t a = umma_desc_k_sw128(s0 + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+            // MODE 0: dQ = dS K (B = K = fA).  MODE 1: dV = P^T dO (B = dO = fB)
+            const uint64_t b = umma_desc_mn_sw128((MODE == 0 ? bq : bdo) + (uint32_t)ks * 2048u, 1024);
+            umma_bf16(tmem_base + colS, a, b, idesc, ks > 0);
+          }
+          if (MODE == 1) {
+            for (int ks = 0; ks < ksteps; ++ks) {  // dK = dS^T Q (B = Q = fA)
+              const uint64_t a = umma_desc_k_sw128(s1 + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+              const uint64_t b = umma_desc_mn_sw128(bq + (uint32_t)ks * 2048u, 1024);
+              umma_bf16(tmem_base + colDP, a, b, idesc, ks > 0);
+            }
+          }
+          umma_commit(out_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, half = warp >> 2;
+    const int rl = q * 32 + lane;
+    const uint32_t x7 = (uint32_t)rl & 7u;
+    const uint32_t row0_s = smem_u32(st0) + (uint32_t)rl * 128u, row1_s = smem_u32(st1) + (uint32_t)rl * 128u;
+    for (int i = 0; i < n_items; ++i) {
+      int n, h, mt;
+      item_coords(i, n, h, mt);
+      const uint32_t par = (uint32_t)i & 1u;
+      const int row = mt * 128 + rl;  // MODE 0: query index; MODE 1: key index
+      const size_t sidx = ((size_t)n * p.heads + h) * p.T;
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+      float Lr = 0.f, Dr = 0.f;
+      if (MODE == 0) {
+        if (row < p.T) { Lr = p.lse[sidx + row]; Dr = p.delta[sidx + row]; }
+      } else {
+        // the previous item's reads of sL/sD are ordered before this point by its ds_full arrive + the
+        // epilogue; a named barrier makes the new values visible to all 128 threads
+        for (int t = threadIdx.x; t < 256; t += TC_SOFTMAX_WARPS * 32) {
+          sL[t] = t < p.T ? p.lse[sidx + t] : 0.f;
+          sD[t] = t < p.T ? p.delta[sidx + t] : 0.f;
+        }
+        asm volatile("bar.sync 5, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
+      }
+      mbar_wait(sd_full, par);
+      tc_fence_after();
+      for (int c = half * 32; c < Tk; c += 64) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tlane + colS + (uint32_t)c, rs);
+        tmem_ld32(tlane + colDP + (uint32_t)c, rd);
+        tc_wait_ld();
+        float pv[32], dv[32];
+        const bool full = !CAUSAL && c + 32 <= p.T;  // whole chunk visible (rows >= T produce unused values)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c + j;  // MODE 0: key index; MODE 1: query index
+          bool ok = true;
+          float L, Dl;
+          if (MODE == 0) {
+            if (!full) ok = col < p.T && (!CAUSAL || col <= row);
+            L = Lr; Dl = Dr;
+          } else {
+            if (!full) ok = col < p.T && (!CAUSAL || row <= col);
+            L = sL[col & 255]; Dl = sD[col & 255];
+          }
+          const float e = fast_exp2(__uint_as_float(rs[j]) * p.c1 - L);
+          const float pr = (ok && row < p.T) ? e : 0.f;
+          pv[j] = pr;
+          dv[j] = pr * (__uint_as_float(rd[j]) - Dl);
+        }
+        const uint32_t boff = (uint32_t)(c >> 6) * 16384u;
+        const uint32_t ch0 = (uint32_t)(c & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = boff + (((ch0 + j) ^ x7) << 4);
+          if (MODE == 0) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row0_s + off),
+                         "r"(pack_bf16(dv[8 * j], dv[8 * j + 1])), "r"(pack_bf16(dv[8 * j + 2], dv[8 * j + 3])),
+                         "r"(pack_bf16(dv[8 * j + 4], dv[8 * j + 5])), "r"(pack_bf16(dv[8 * j + 6], dv[8 * j + 7]))
+                         : "memory");
+          } else {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row0_s + off),
+                         "r"(pack_bf16(pv[8 * j], pv[8 * j + 1])), "r"(pack_bf16(pv[8 * j + 2], pv[8 * j + 3])),
+                         "r"(pack_bf16(pv[8 * j + 4], pv[8 * j + 5])), "r"(pack_bf16(pv[8 * j + 6], pv[8 * j + 7]))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row1_s + off),
+                         "r"(pack_bf16(dv[8 * j], dv[8 * j + 1])), "r"(pack_bf16(dv[8 * j + 2], dv[8 * j + 3])),
+                         "r"(pack_bf16(dv[8 * j + 4], dv[8 * j + 5])), "r"(pack_bf16(dv[8 * j + 6], dv[8 * j + 7]))
+                         : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      // ---- epilogue
+      mbar_wait(out_full, par);
+      tc_fence_after();
+      const size_t grow = ((size_t)n * p.T + row) * (3 * (size_t)D) + h * HD;
+#pragma unroll
+      for (int part = 0; part < (MODE == 0 ? 1 : 2); ++part) {
+        // MODE 0: dQ (scaled) -> q part.  MODE 1: part 0 = dV -> v part, part 1 = dK (scaled) -> k part
+        const uint32_t colbase = part == 0 ? colS : colDP;
+        const float sc = (MODE == 0 || part == 1) ? p.scale : 1.f;
+        bf16* dst = p.dqkv + grow + (MODE == 0 ? 0 : (part == 0 ? 2 * D : D));
+        {
+          const int c = half * 32;  // each warp of the pair writes 32 of the 64 head-dim columns
+          uint32_t r[32];
+          tmem_ld32(tlane + colbase + (uint32_t)c, r);
+          tc_wait_ld();
+          if (row < p.T) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(r[8 * j]) * sc, __uint_as_float(r[8 * j + 1]) * sc);
+              v.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * sc, __uint_as_float(r[8 * j + 3]) * sc);
+              v.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * sc, __uint_as_float(r[8 * j + 5]) * sc);
+              v.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * sc, __uint_as_float(r[8 * j + 7]) * sc);
+              *reinterpret_cast<uint4*>(dst + c + 8 * j) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(item_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_SOFTMAX_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int MODE, bool CAUSAL>
+int launch_bwd_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d,
+                  const AttnBwdTcParams& p, cudaStream_t st) {
+  const int nkb = (p.Tk + 63) / 64;
+  const size_t smem = 2 * 16384 + 2 * (size_t)p.Tk * 128 + (size_t)(MODE == 1 ? 2 : 1) * nkb * 16384 + 2048 + 128 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = p.total_items < g_attn_sms ? p.total_items : g_attn_sms;
+  attn_bwd_tc_kernel<MODE, CAUSAL><<<grid, TC_THREADS, smem, st>>>(a, b, c, d, p);
+  return MFK_OK;
+}
+}  // namespace
+
+extern "C" int mfk_attn_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
+                               void* dqkv, int N, int T, int heads, int causal, void* stream) {
+  if (!qkv || !out || !d_out || !lse || !delta_ws || !dqkv || N <= 0 || T <= 0) return MFK_EARG;
+  if (T > 240) return MFK_ESHAPE;  // staged P^T + dS^T + Q + dO exceed 227 KB of smem beyond 240 keys
+  if (g_attn_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_attn_sms <= 0) g_attn_sms = 148;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = heads * HD;
+  const long long rows = (long long)N * T;
+  const long long warps = rows * heads;
+  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(static_cast<const bf16*>(out),
+                                                                  static_cast<const bf16*>(d_out), delta_ws, T, heads, rows);
+  AttnBwdTcParams p;
+  p.lse = lse; p.delta = delta_ws; p.dqkv = static_cast<bf16*>(dqkv);
+  p.T = T; p.Tk = (T + 15) / 16 * 16; p.heads = heads;
+  p.m_tiles = (T + 127) / 128;
+  p.total_items = N * heads * p.m_tiles;
+  p.c1 = 0.125f * kLog2e; p.scale = 0.125f;
+  CUtensorMap tmTile, tmFull, tmDoTile, tmDoFull;
+  int rc;
+  if ((rc = mfk_make_tmap_2d(&tmTile, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, 128, 64, 128)) != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmFull, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, (uint32_t)p.Tk, 64, 128)) != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmDoTile, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, 128, 64, 128)) != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmDoFull, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, (uint32_t)p.Tk, 64, 128)) != MFK_OK) return rc;
+  if (causal) {
+    if ((rc = launch_bwd_tc<0, true>(tmTile, tmFull, tmDoTile, tmDoFull, p, st)) != MFK_OK) return rc;
+    if ((rc = launch_bwd_tc<1, true>(tmTile, tmFull, tmDoTile, tmDoFull, p, st)) != MFK_OK) return rc;
+  } else {
+    if ((rc = launch_bwd_tc<0, false>(tmTile, tmFull, tmDoTile, tmDoFull, p, st)) != MFK_OK) return rc;
+    if ((rc = launch_bwd_tc<1, false>(tmTile, tmFull, tmDoTile, tmDoFull, p, st)) != MFK_OK) return rc;
+  }
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}

@@ -77,7 +77,7 @@ ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ rowidx, const
 // dx = rstd * (dy*g - mean_D(dy*g) - xhat * mean_D(dy*g*xhat));  g_out = g_in + dx.
 // dgamma/dbeta: per-CTA partial column sums (deterministic two-stage reduction).
 template <int VEC, bool DY_BF16>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ mean_i,
               const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* g_in,
               float* g_out, bf16* __restrict__ g16, float* __restrict__ partial, int M) {
@@ -422,7 +422,7 @@ extern "C" int mfk_layernorm_fwd(const float* x, const int* rowidx, const float*
 
 extern "C" int mfk_ln_bwd_ctas(int M) {
   int g = (M + kLnWarps - 1) / kLnWarps;
-  return g < 296 ? g : 296;  // 2 CTAs per SM on 148 SMs
+  return g < 592 ? g : 592;  // 4 CTAs per SM on 148 SMs (2 resident at a time)
 }
 
 extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,

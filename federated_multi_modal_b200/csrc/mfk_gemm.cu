@@ -68,7 +68,9 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0,
   n0 = (big % p.n_big) * p.bn + sub * w;
 }
 
-template <int BN, int kStages>
+// kMN = false: A[M,K], B[N,K] (K contiguous; "TN").  kMN = true: A given as [K,M], B as [K,N] (M / N contiguous:
+// MN-major UMMA operands) — the wgrad form dW = dY^T X straight from the row-major activations, no transposes.
+template <int BN, int kStages, bool kMN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -131,9 +133,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
-          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
-          for (int j = 0; j < w; j += BOXN)
-            tma_load_2d(&tmB, &full_bar[stage], sb + j * (BK * 2), kb * BK, n0 + j);
+          if (!kMN) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+            for (int j = 0; j < w; j += BOXN)
+              tma_load_2d(&tmB, &full_bar[stage], sb + j * (BK * 2), kb * BK, n0 + j);
+          } else {
+            // boxes of 64 (M or N, contiguous) x 64 K-rows = 8 KB, one per 64-wide MN group
+            for (int j = 0; j < BM; j += 64)
+              tma_load_2d(&tmA, &full_bar[stage], sa + j * 128, m0 + j, kb * BK);
+            for (int j = 0; j < w; j += 64)
+              tma_load_2d(&tmB, &full_bar[stage], sb + j * 128, n0 + j, kb * BK);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -152,19 +162,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(BM, w, 0, 0);
+        const uint32_t idesc = umma_idesc_bf16(BM, w, kMN ? 1 : 0, kMN ? 1 : 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+          const uint64_t adesc = kMN ? umma_desc_mn_sw128(sa, 8192) : umma_desc_k_sw128(sa);
+          const uint64_t bdesc = kMN ? umma_desc_mn_sw128(sa + kABytes, 8192) : umma_desc_k_sw128(sa + kABytes);
+          // per UMMA_K = 16: K-major advances 32 B inside the swizzle row (+2 in 16-byte units); MN-major
+          // advances 16 K-rows of 128 B (+128 in 16-byte units)
+          constexpr uint64_t kStep = kMN ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            // advance 16 elements (32 B) inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -387,19 +398,19 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int kStages>
+template <int BN, int kStages, bool kMN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO32,
                        const CUtensorMap& tmO16, const CUtensorMap& tmPre, const GemmParams& p, int grid,
                        cudaStream_t st) {
   static bool configured = false;
   constexpr size_t smem = gemm_smem_bytes<BN, kStages>();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages, kMN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  gemm_bf16_tn_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(tmA, tmB, tmO32, tmO16, tmPre, p);
+  gemm_bf16_tn_kernel<BN, kStages, kMN><<<grid, kThreads, smem, st>>>(tmA, tmB, tmO32, tmO16, tmPre, p);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -458,6 +469,36 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
     return rc;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
-  return launch_gemm<128, 6>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+  if (bn == 256) return launch_gemm<256, 4, false>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+  return launch_gemm<128, 6, false>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+}
+
+// out[M,N] (fp32) = At^T * Bt with At[K,M], Bt[K,N] bf16 row-major (leading dimensions lda, ldb >= M, N).
+extern "C" int mfk_gemm_bf16_at_b(const void* At, long long lda, const void* Bt, long long ldb, int M, int N, int K,
+                                  float* out_f32, long long ld32, void* stream) {
+  if (!At || !Bt || !out_f32 || M <= 0 || N <= 0 || K <= 0) return MFK_EARG;
+  if (N % 32 != 0 || lda % 8 != 0 || ldb % 8 != 0 || lda < M || ldb < N) return MFK_ESHAPE;
+  if (ld32 % 4 || !mfk_aligned16(out_f32)) return MFK_EALIGN;
+  const int sms = num_sms();
+  const int m_tiles = (M + BM - 1) / BM;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bn = 256;
+  p.n_big = (N + 255) / 256;
+  const int big = m_tiles * p.n_big;
+  p.full_tiles = (big / sms) * sms;
+  const int rem = big - p.full_tiles;
+  p.split = 1;
+  if (rem > 0)
+    while (p.split * 2 <= 4 && rem * p.split * 2 <= sms) p.split *= 2;
+  p.total_tiles = p.full_tiles + rem * p.split;
+  p.out32 = out_f32; p.ld32 = ld32;
+  CUtensorMap tmA, tmB, tmO32;
+  int rc = mfk_make_tmap_2d(&tmA, At, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 64, 128);
+  if (rc != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmB, Bt, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64, 128)) != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmO32, out_f32, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ld32, 32, 32, 128)) != MFK_OK)
+    return rc;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  return launch_gemm<256, 4, true>(tmA, tmB, tmO32, tmA, tmA, p, grid, static_cast<cudaStream_t>(stream));
 }

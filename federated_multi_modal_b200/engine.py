@@ -228,10 +228,6 @@ class MapleEngine:
             ws["delta"] = b("delta", (N * tw.heads * T,), F32)
             ws["lnp"] = b("lnp", (2 * D * ops.ln_bwd_ctas(M),), F32)
             ws["csum"] = b("csum", (32 * 4 * D,), F32)
-            if self.wgrad_last:
-                Mp = (M + 7) // 8 * 8
-                ws["tA"] = b("tA", (4 * D, Mp), BF16)
-                ws["tB"] = b("tB", (4 * D, Mp), BF16)
 
     # ------------------------------------------------------------------ prompt learner
     def _prompt_learner_fwd(self):
@@ -287,14 +283,8 @@ class MapleEngine:
         return out
 
     def _wgrad(self, tw: _Tower, dy16, x16, dW, Nout, Kin):
-        """dW[Nout,Kin] = dy^T x via two K-major transposes and the same tcgen05 GEMM."""
-        ws, M = tw.ws, tw.M
-        Mp = (M + 7) // 8 * 8
-        tA = ws["tA"].view(-1)[:Nout * Mp].view(Nout, Mp)
-        tB = ws["tB"].view(-1)[:Kin * Mp].view(Kin, Mp)
-        ops.transpose_bf16(dy16, tA)
-        ops.transpose_bf16(x16, tB)
-        ops.gemm(tA, tB, out_f32=dW, k=M)
+        """dW[Nout,Kin] = dy^T x straight from the row-major bf16 activations (MN-major UMMA operands)."""
+        ops.gemm_at_b(dy16, x16, dW)
 
     def _block_bwd(self, tw: _Tower, l: int):
         ws, w, D, M = tw.ws, tw.w[l], tw.D, tw.M

@@ -37,13 +37,27 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          out_f32, ld(out_f32), out_bf16, ld(out_bf16), out_pre, ld(out_pre), tile_n, stream_ptr())
 
 
-def attn_fwd(qkv, out, lse, N, T, heads, causal):
+def gemm_at_b(at: torch.Tensor, bt: torch.Tensor, out_f32: torch.Tensor):
+    """out[M,N] = at[K,M]^T @ bt[K,N] (bf16 in, fp32 out): wgrad straight from row-major dY and X."""
+    _chk(at, BF16, "at"); _chk(bt, BF16, "bt")
+    call("mfk_gemm_bf16_at_b", at, at.stride(0), bt, bt.stride(0), at.shape[1], bt.shape[1], at.shape[0], out_f32,
+         out_f32.stride(0), stream_ptr())
+
+
+TC_ATTN_MIN_T = 65  # sequences longer than this use the tcgen05 attention kernels
+
+
+def attn_fwd(qkv, out, lse, N, T, heads, causal, impl: Optional[str] = None):
+    """impl: None = by sequence length, "tc" = tcgen05/TMEM kernel, "mma" = warp-level mma.sync kernel."""
     _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out")
-    call("mfk_attn_fwd", qkv, out, lse, N, T, heads, int(causal), stream_ptr())
+    use_tc = (T >= TC_ATTN_MIN_T) if impl is None else impl == "tc"
+    call("mfk_attn_fwd_tc" if use_tc else "mfk_attn_fwd", qkv, out, lse, N, T, heads, int(causal), stream_ptr())
 
 
-def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal):
-    call("mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, int(causal), stream_ptr(), kernels=3)
+def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal, impl: Optional[str] = None):
+    use_tc = (TC_ATTN_MIN_T <= T <= 240) if impl is None else impl == "tc"
+    call("mfk_attn_bwd_tc" if use_tc else "mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads,
+         int(causal), stream_ptr(), kernels=3)
 
 
 def layernorm_fwd(x, gamma, beta, *, rowidx=None, y_bf16=None, y_f32=None, x_save=None, mean=None, rstd=None,

@@ -41,6 +41,12 @@ int mfk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, in
                   long long ldres, float* out_f32, long long ld32, void* out_bf16, long long ld16,
                   void* out_pre_bf16, long long ldpre, int tile_n, void* stream);
 
+/* out[M,N] fp32 = At^T * Bt, At[K,M] and Bt[K,N] bf16 row-major (MN-major UMMA operands, no transposes).
+ * The wgrad form of autograd for the trainable resblocks.11 (trainers/maple.py:472-474,590):
+ * dW[out,in] = dY[rows,out]^T X[rows,in].                                                             */
+int mfk_gemm_bf16_at_b(const void* At, long long lda, const void* Bt, long long ldb, int M, int N, int K,
+                       float* out_f32, long long ld32, void* stream);
+
 /* ------------------------------------------------------------------ attention (head dim 64, T <= 256)
  * qkv[N*T, 3*heads*64] bf16 (q|k|v, head h = columns h*64..h*64+63 of each part) -> out[N*T, heads*64].
  * softmax(q k^T / 8 [+ causal mask]) v per (sequence, head). lse[N,heads,T] (log2 domain) is saved for
@@ -48,9 +54,14 @@ int mfk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, in
  * ResidualAttentionBlock_MaPLe.attention (clip/model.py:303-305) with the additive causal mask of
  * CLIP.build_attention_mask (clip/model.py:679-685) when causal != 0.                                 */
 int mfk_attn_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int causal, void* stream);
+/* Same contract as mfk_attn_fwd on the tcgen05/TMEM/TMA path (S = QK^T and O = PV as UMMA tiles, softmax one
+ * TMEM lane per query row); used for long sequences (the 199-token vision tower).                      */
+int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int heads, int causal, void* stream);
 /* dqkv[N*T, 3*heads*64] bf16 from d_out; delta_ws: N*heads*T floats of scratch. */
 int mfk_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
                  void* dqkv, int N, int T, int heads, int causal, void* stream);
+int mfk_attn_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
+                    void* dqkv, int N, int T, int heads, int causal, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm (clip/model.py:153-159)
  * fp32 statistics, eps as given (1e-5), D in {128, 512, 768}. rowidx (int32[M], may be NULL) gathers

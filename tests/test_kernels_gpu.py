@@ -86,6 +86,17 @@ def test_gemm_padded_k_operands():
     assert (out - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K", [(768, 3072, 6368), (3072, 768, 6368), (512, 512, 100), (1536, 512, 770),
+                                   (128, 64, 64), (200, 96, 1000)])
+def test_gemm_at_b_wgrad_form(M, N, K):
+    at, bt = rnd(K, M, dtype=BF16, seed=60), rnd(K, N, dtype=BF16, seed=61)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=F32)
+    ops.gemm_at_b(at, bt, out)
+    ref = at.float().t() @ bt.float()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
 def _attn_ref(qkv, N, T, heads, causal):
     D = heads * 64
     q, k, v = qkv.float().reshape(N, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
@@ -100,12 +111,13 @@ def _attn_ref(qkv, N, T, heads, causal):
 @pytest.mark.parametrize("N,T,heads,causal", [(2, 199, 12, False), (3, 77, 8, True), (4, 16, 8, True),
                                               (2, 64, 2, False), (1, 256, 1, True), (5, 11, 8, True),
                                               (32, 199, 12, False)])
-def test_attention_fwd_bwd(N, T, heads, causal):
+@pytest.mark.parametrize("impl", ["mma", "tc"])
+def test_attention_fwd_bwd(N, T, heads, causal, impl):
     D = heads * 64
     qkv = rnd(N * T, 3 * D, dtype=BF16, seed=9)
     out = torch.empty(N * T, D, device=DEV, dtype=BF16)
     lse = torch.empty(N, heads, T, device=DEV, dtype=F32)
-    ops.attn_fwd(qkv, out, lse, N, T, heads, causal)
+    ops.attn_fwd(qkv, out, lse, N, T, heads, causal, impl=impl)
     x = qkv.float().requires_grad_(True)
     o_ref, p, _ = _attn_ref(x, N, T, heads, causal)
     assert (out.float() - o_ref).abs().max().item() < 2e-2
@@ -113,7 +125,11 @@ def test_attention_fwd_bwd(N, T, heads, causal):
     o_ref.backward(d_out.float())
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(N * heads * T, device=DEV, dtype=F32)
-    ops.attn_bwd(qkv, out, d_out, lse, delta, dqkv, N, T, heads, causal)
+    if impl == "tc" and T > 240:
+        with pytest.raises(RuntimeError, match="unsupported shape"):
+            ops.attn_bwd(qkv, out, d_out, lse, delta, dqkv, N, T, heads, causal, impl="tc")
+        impl = None  # dispatch by length: falls to the warp-level kernel beyond 240 keys
+    ops.attn_bwd(qkv, out, d_out, lse, delta, dqkv, N, T, heads, causal, impl=impl)
     err = (dqkv.float() - x.grad).abs().max().item()
     assert err < 3e-2 * max(1.0, x.grad.abs().max().item()), err
 
