@@ -26,6 +26,7 @@ SIGNATURES = {
     "mfk_attn_fwd_tc": [P, P, P, I, I, I, I, P],
     "mfk_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P],
     "mfk_attn_bwd_tc": [P, P, P, P, P, P, I, I, I, I, P],
+    "mfk_attn_bwd_fused": [P, P, P, P, P, P, I, I, I, P],
     "mfk_layernorm_fwd": [P, P, P, P, P, P, P, P, P, I, I, F, P],
     "mfk_ln_bwd_ctas": [I],
     "mfk_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, I, I, I, P],

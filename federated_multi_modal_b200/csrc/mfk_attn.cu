@@ -205,18 +205,29 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
 // ============================================================================ backward: delta = rowsum(dO * O)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
                                   int T, int heads, long long rows) {
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (row, head)
+  // one warp per token row: 16-byte loads, 8 lanes cover one head (64 elements), shuffle-reduce inside the octet
+  pdl_trigger();
+  pdl_wait();
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (w >= rows * heads) return;
-  const long long row = w / heads;
-  const int h = (int)(w % heads);
-  const size_t off = (size_t)row * heads * HD + h * HD + lane * 2;
-  float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + off));
-  float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(d_o + off));
-  float s = warp_sum(a.x * b.x + a.y * b.y);
-  if (lane == 0) {
-    const long long n = row / T, t = row % T;
-    delta[((size_t)n * heads + h) * T + t] = s;
+  if (row >= rows) return;
+  const int chunks = heads * 8;  // 16-byte chunks per row
+  const uint4* po = reinterpret_cast<const uint4*>(o + (size_t)row * heads * HD);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + (size_t)row * heads * HD);
+  const long long n = row / T, t = row % T;
+  for (int c = lane; c < ((chunks + 31) & ~31); c += 32) {
+    float s = 0.f;
+    if (c < chunks) {
+      const uint4 a = po[c], b = pd[c];
+      const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+      const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+      s = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
+          (a3.x * b3.x + a3.y * b3.y);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0 && c < chunks) delta[((size_t)n * heads + (c >> 3)) * T + t] = s;
   }
 }
 
@@ -381,7 +392,7 @@ extern "C" int mfk_attn_bwd(const void* qkv, const void* out, const void* d_out,
   const int Tp = ((T + TILE - 1) / TILE) * TILE;
   const long long rows = (long long)N * T;
   const long long warps = rows * heads;
-  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ST(stream)>>>(static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta_ws, T, heads, rows);
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta_ws, T, heads, rows);
   const size_t smem_dq = 2 * (size_t)TILE * 128 + 2 * (size_t)Tp * 128;
   const size_t smem_dkv = smem_dq + 2 * (size_t)Tp * sizeof(float);
   dim3 grid(Tp / TILE, heads, N);
@@ -481,6 +492,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   auto item_coords = [&](int i, int& n, int& h, int& mt) {
     const int w = (int)blockIdx.x + i * (int)gridDim.x;
@@ -678,11 +691,13 @@ extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, in
   if (causal) {
     e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attn_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+    e = launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), smem, static_cast<cudaStream_t>(stream), tmQ, tmKV, p);
+    if (e != cudaSuccess) return (int)e;
   } else {
     e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attn_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+    e = launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), smem, static_cast<cudaStream_t>(stream), tmQ, tmKV, p);
+    if (e != cudaSuccess) return (int)e;
   }
   MFK_CHECK_LAUNCH();
   return MFK_OK;
@@ -974,7 +989,7 @@ extern "C" int mfk_attn_bwd_tc(const void* qkv, const void* out, const void* d_o
   const int D = heads * HD;
   const long long rows = (long long)N * T;
   const long long warps = rows * heads;
-  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(static_cast<const bf16*>(out),
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(static_cast<const bf16*>(out),
                                                                   static_cast<const bf16*>(d_out), delta_ws, T, heads, rows);
   AttnBwdTcParams p;
   p.lse = lse; p.delta = delta_ws; p.dqkv = static_cast<bf16*>(dqkv);
@@ -996,5 +1011,290 @@ extern "C" int mfk_attn_bwd_tc(const void* qkv, const void* out, const void* d_o
     if ((rc = launch_bwd_tc<1, false>(tmTile, tmFull, tmDoTile, tmDoFull, p, st)) != MFK_OK) return rc;
   }
   MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+// =====================================================================================================
+// Fused tcgen05 attention BACKWARD: one work unit = one (sequence, head); Q, K, V, dO are loaded ONCE into smem
+// and every 128x128 (query tile i, key tile j) block computes S, dP once:
+//     S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T   (K-major operands)        -> TMEM cols [0,128) / [128,256)
+//     P, dS (bf16) staged in swizzled smem by 8 warps (one TMEM lane = one query row per thread)
+//     dV_j += P^T dO_i, dK_j += dS^T Q_i      (staged tile as MN-major A, dO_i / Q_i as MN-major B)
+//     dQ_i += dS K_j                           (staged tile as K-major A,  K_j as MN-major B)
+// Accumulators: dQ_0, dQ_1, dK_j, dV_j live in TMEM cols [256,512). tcgen05.commit ordering is used so that the
+// S/dP MMAs of block k+1 are queued right behind the second-stage MMAs of block k. Deterministic (no atomics).
+namespace {
+using namespace mfk;
+
+struct AttnBwdFusedParams {
+  const float* lse;
+  const float* delta;
+  bf16* dqkv;
+  int T, R, tiles, heads, total_units;
+  float c1, scale;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmDo,
+                         const AttnBwdFusedParams p) {
+  extern __shared__ uint8_t smem_raw_f[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_f) + 1023) & ~uintptr_t(1023));
+  const int D = p.heads * HD, R = p.R, NT = p.tiles;
+  const uint32_t fullBytes = (uint32_t)R * 128u;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + fullBytes;
+  uint8_t* sV = sK + fullBytes;
+  uint8_t* sdO = sV + fullBytes;
+  uint8_t* sP = sdO + fullBytes;   // [2 column blocks][128 rows x 128 B]
+  uint8_t* sdS = sP + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* ld_full = bars;
+  uint64_t* sd_full = bars + 1;
+  uint64_t* ds_full = bars + 2;
+  uint64_t* mma2_done = bars + 3;
+  uint64_t* dkv_free = bars + 4;
+  uint64_t* unit_free = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = (p.total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nblk = NT * NT;
+
+  if (warp == TC_SOFTMAX_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQkv);
+      tma_prefetch_desc(&tmDo);
+      mbar_init(ld_full, 1);
+      mbar_init(sd_full, 1);
+      mbar_init(ds_full, TC_SOFTMAX_WARPS);
+      mbar_init(mma2_done, 1);
+      mbar_init(dkv_free, TC_SOFTMAX_WARPS);
+      mbar_init(unit_free, TC_SOFTMAX_WARPS);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t colS = 0, colDP = 128, colDQ = 256, colDK = 384, colDV = 448;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == TC_SOFTMAX_WARPS) {
+    if (lane == 0) {
+      uint32_t blk_ctr = 0, kt_ctr = 0;
+      const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_tt = umma_idesc_bf16(128, HD, 1, 1);  // A, B MN-major (dV, dK)
+      const uint32_t idesc_kt = umma_idesc_bf16(128, HD, 0, 1);  // A K-major, B MN-major (dQ)
+      const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), uDo = smem_u32(sdO);
+      const uint32_t uP = smem_u32(sP), uDs = smem_u32(sdS);
+      auto issue_sdp = [&](int i, int j) {
+        const uint64_t aq = umma_desc_k_sw128(uQ + (uint32_t)i * 16384u), bk = umma_desc_k_sw128(uK + (uint32_t)j * 16384u);
+        const uint64_t ad = umma_desc_k_sw128(uDo + (uint32_t)i * 16384u), bv = umma_desc_k_sw128(uV + (uint32_t)j * 16384u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colS, aq + 2ull * k, bk + 2ull * k, idesc1, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colDP, ad + 2ull * k, bv + 2ull * k, idesc1, k > 0);
+        umma_commit(sd_full);
+      };
+      for (int u = 0; u < n_units; ++u) {
+        const int w = (int)blockIdx.x + u * (int)gridDim.x;
+        const int h = w % p.heads, n = w / p.heads;
+        mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
+        mbar_arrive_expect_tx(ld_full, 4u * fullBytes);
+        const int row0 = n * p.T;
+        tma_load_2d(&tmQkv, ld_full, sQ, h * HD, row0);
+        tma_load_2d(&tmQkv, ld_full, sK, D + h * HD, row0);
+        tma_load_2d(&tmQkv, ld_full, sV, 2 * D + h * HD, row0);
+        tma_load_2d(&tmDo, ld_full, sdO, h * HD, row0);
+        mbar_wait(ld_full, (uint32_t)u & 1u);
+        tc_fence_after();
+        issue_sdp(0, 0);
+        for (int k = 0; k < nblk; ++k, ++blk_ctr) {
+          const int j = k / NT, i = k % NT;
+          mbar_wait(ds_full, blk_ctr & 1u);
+          if (i == 0 && j > 0) {  // accumulators of the previous key tile must have been drained
+            mbar_wait(dkv_free, kt_ctr & 1u);
+            ++kt_ctr;
+          }
+          tc_fence_after();
+          for (int ks = 0; ks < 8; ++ks) {  // dV_j += P^T dO_i   (K = 128 query rows, 16 per MMA)
+            const uint64_t a = umma_desc_mn_sw128(uP + (uint32_t)ks * 2048u, 16384);
+            const uint64_t b = umma_desc_mn_sw128(uDo + (uint32_t)i * 16384u + (uint32_t)ks * 2048u, 1024);
+            umma_bf16(tmem_base + colDV, a, b, idesc_tt, (i > 0 || ks > 0));
+          }
+          for (int ks = 0; ks < 8; ++ks) {  // dK_j += dS^T Q_i
+            const uint64_t a = umma_desc_mn_sw128(uDs + (uint32_t)ks * 2048u, 16384);
+            const uint64_t b = umma_desc_mn_sw128(uQ + (uint32_t)i * 16384u + (uint32_t)ks * 2048u, 1024);
+            umma_bf16(tmem_base + colDK, a, b, idesc_tt, (i > 0 || ks > 0));
+          }
+          for (int ks = 0; ks < 8; ++ks) {  // dQ_i += dS K_j        (K = 128 keys)
+            const uint64_t a = umma_desc_k_sw128(uDs + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+            const uint64_t b = umma_desc_mn_sw128(uK + (uint32_t)j * 16384u + (uint32_t)ks * 2048u, 1024);
+            umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, a, b, idesc_kt, (j > 0 || ks > 0));
+          }
+          umma_commit(mma2_done);
+          if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
+        }
+        // the last key tile's dkv_free arrive is consumed here so the phase counters stay in step
+        mbar_wait(dkv_free, kt_ctr & 1u);
+        ++kt_ctr;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, half = warp >> 2;
+    const int rl = q * 32 + lane;
+    const uint32_t x7 = (uint32_t)rl & 7u;
+    const uint32_t prow = smem_u32(sP) + (uint32_t)rl * 128u, dsrow = smem_u32(sdS) + (uint32_t)rl * 128u;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t blk_ctr = 0;
+    for (int u = 0; u < n_units; ++u) {
+      const int w = (int)blockIdx.x + u * (int)gridDim.x;
+      const int h = w % p.heads, n = w / p.heads;
+      const size_t sidx = ((size_t)n * p.heads + h) * p.T;
+      for (int k = 0; k < nblk; ++k, ++blk_ctr) {
+        const int j = k / NT, i = k % NT;
+        const int qrow = i * 128 + rl;
+        const bool qok = qrow < p.T;
+        const float L = qok ? p.lse[sidx + qrow] : 0.f, Dl = qok ? p.delta[sidx + qrow] : 0.f;
+        mbar_wait(sd_full, blk_ctr & 1u);  // also implies the previous block's second-stage MMAs retired
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 32 + cc * 64;
+          uint32_t rs[32], rd[32];
+          tmem_ld32(tlane + colS + (uint32_t)c, rs);
+          tmem_ld32(tlane + colDP + (uint32_t)c, rd);
+          tc_wait_ld();
+          float pv[32], dv[32];
+          const int key0 = j * 128 + c;
+          const bool full = key0 + 32 <= p.T;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float e = fast_exp2(__uint_as_float(rs[jj]) * p.c1 - L);
+            const float pr = (qok && (full || key0 + jj < p.T)) ? e : 0.f;
+            pv[jj] = pr;
+            dv[jj] = pr * (__uint_as_float(rd[jj]) - Dl);
+          }
+          const uint32_t boff = (uint32_t)(c >> 6) * 16384u;
+          const uint32_t ch0 = (uint32_t)(c & 63) >> 3;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t off = boff + (((ch0 + t) ^ x7) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + off),
+                         "r"(pack_bf16(pv[8 * t], pv[8 * t + 1])), "r"(pack_bf16(pv[8 * t + 2], pv[8 * t + 3])),
+                         "r"(pack_bf16(pv[8 * t + 4], pv[8 * t + 5])), "r"(pack_bf16(pv[8 * t + 6], pv[8 * t + 7]))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dsrow + off),
+                         "r"(pack_bf16(dv[8 * t], dv[8 * t + 1])), "r"(pack_bf16(dv[8 * t + 2], dv[8 * t + 3])),
+                         "r"(pack_bf16(dv[8 * t + 4], dv[8 * t + 5])), "r"(pack_bf16(dv[8 * t + 6], dv[8 * t + 7]))
+                         : "memory");
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_full);
+        if (i == NT - 1) {
+          // ---- key tile j complete: dK_j (scaled), dV_j -> global
+          mbar_wait(mma2_done, blk_ctr & 1u);
+          tc_fence_after();
+          const int key = j * 128 + rl;
+          const size_t grow = ((size_t)n * p.T + key) * (3 * (size_t)D) + h * HD + half * 32;
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            uint32_t r[32];
+            tmem_ld32(tlane + (part == 0 ? colDK : colDV) + (uint32_t)(half * 32), r);
+            tc_wait_ld();
+            if (key < p.T) {
+              const float sc = part == 0 ? p.scale : 1.f;
+              bf16* dst = p.dqkv + grow + (part == 0 ? D : 2 * D);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(r[8 * t]) * sc, __uint_as_float(r[8 * t + 1]) * sc);
+                v.y = pack_bf16(__uint_as_float(r[8 * t + 2]) * sc, __uint_as_float(r[8 * t + 3]) * sc);
+                v.z = pack_bf16(__uint_as_float(r[8 * t + 4]) * sc, __uint_as_float(r[8 * t + 5]) * sc);
+                v.w = pack_bf16(__uint_as_float(r[8 * t + 6]) * sc, __uint_as_float(r[8 * t + 7]) * sc);
+                *reinterpret_cast<uint4*>(dst + 8 * t) = v;
+              }
+            }
+          }
+          if (j == NT - 1) {
+            // ---- unit complete: dQ_i (scaled) -> global
+            for (int ii = 0; ii < NT; ++ii) {
+              uint32_t r[32];
+              tmem_ld32(tlane + colDQ + (uint32_t)ii * 64u + (uint32_t)(half * 32), r);
+              tc_wait_ld();
+              const int qr = ii * 128 + rl;
+              if (qr < p.T) {
+                bf16* dst = p.dqkv + ((size_t)n * p.T + qr) * (3 * (size_t)D) + h * HD + half * 32;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  uint4 v;
+                  v.x = pack_bf16(__uint_as_float(r[8 * t]) * p.scale, __uint_as_float(r[8 * t + 1]) * p.scale);
+                  v.y = pack_bf16(__uint_as_float(r[8 * t + 2]) * p.scale, __uint_as_float(r[8 * t + 3]) * p.scale);
+                  v.z = pack_bf16(__uint_as_float(r[8 * t + 4]) * p.scale, __uint_as_float(r[8 * t + 5]) * p.scale);
+                  v.w = pack_bf16(__uint_as_float(r[8 * t + 6]) * p.scale, __uint_as_float(r[8 * t + 7]) * p.scale);
+                  *reinterpret_cast<uint4*>(dst + 8 * t) = v;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(dkv_free);
+            if (j == NT - 1) mbar_arrive(unit_free);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_SOFTMAX_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace
+
+extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* d_out, const float* lse,
+                                  float* delta_ws, void* dqkv, int N, int T, int heads, void* stream) {
+  if (!qkv || !out || !d_out || !lse || !delta_ws || !dqkv || N <= 0 || T <= 0 || T > 256) return MFK_EARG;
+  if (g_attn_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_attn_sms <= 0) g_attn_sms = 148;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = heads * HD;
+  const long long rows = (long long)N * T;
+  const long long warps = rows * heads;
+  cudaError_t e = launch_pdl(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st,
+                             static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta_ws, T, heads, rows);
+  if (e != cudaSuccess) return (int)e;
+  AttnBwdFusedParams p;
+  p.lse = lse; p.delta = delta_ws; p.dqkv = static_cast<bf16*>(dqkv);
+  p.T = T; p.tiles = (T + 127) / 128; p.R = p.tiles * 128; p.heads = heads;
+  p.total_units = N * heads;
+  p.c1 = 0.125f * kLog2e; p.scale = 0.125f;
+  CUtensorMap tmQkv, tmDo;
+  int rc;
+  if ((rc = mfk_make_tmap_2d(&tmQkv, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmDo, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;
+  const size_t smem = 4 * (size_t)p.R * 128 + 65536 + 128 + 1024;
+  e = cudaFuncSetAttribute(attn_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = p.total_units < g_attn_sms ? p.total_units : g_attn_sms;
+  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmQkv, tmDo, p);
+  if (e != cudaSuccess) return (int)e;
   return MFK_OK;
 }

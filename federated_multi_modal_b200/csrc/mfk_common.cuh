@@ -56,6 +56,13 @@ __device__ __forceinline__ float dquickgelu(float u) {
   return s * (1.0f + 1.702f * u * (1.0f - s));
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Kernels launched through mfk::launch_pdl may start (and run their prologue) while the previous kernel of
+// the stream is still draining; pdl_wait() blocks until that kernel has completed and its writes are visible.
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -189,6 +196,25 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a
   return d;
 }
 
+}  // namespace mfk
+
+namespace mfk {
+// Host: launch with the programmatic-stream-serialization attribute (PDL); works inside CUDA graph capture.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace mfk
 
 // Host: encode a 2-D bf16 row-major tensor map with 128-byte swizzle (box inner = 64 elements).

@@ -51,6 +51,8 @@ ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ rowidx, const
               const float* __restrict__ beta, bf16* __restrict__ y16, float* __restrict__ y32,
               float* __restrict__ xsave, float* __restrict__ mean_o, float* __restrict__ rstd_o, int M, float eps) {
   constexpr int D = 128 * VEC;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -83,6 +85,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
               float* g_out, bf16* __restrict__ g16, float* __restrict__ partial, int M) {
   constexpr int D = 128 * VEC;
   __shared__ __align__(16) float red[kLnWarps][D];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4 dg[VEC], db[VEC];
@@ -150,24 +154,26 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
   }
 }
 
-// out[c] (+)= sum_p partial[p, c]. block (32, 8): 8 row groups sum P/8 partials each (strided, fixed order),
-// then a fixed-order 8-way combine. Two outputs (dgamma | dbeta) are handled by blockIdx.y.
+// out[c] (+)= sum_p partial[p, c]. block (32, 32): 32 row groups sum P/32 partials each (strided, fixed order),
+// then a fixed-order 32-way combine. Two outputs (dgamma | dbeta) are handled by blockIdx.y.
 __global__ void partial_reduce_kernel(const float* __restrict__ partial, int P, int N, long long pstride,
                                       long long ystride, float* __restrict__ out0, float* __restrict__ out1,
                                       int accumulate) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x;
   float* out = blockIdx.y == 0 ? out0 : out1;
   const float* src = partial + (size_t)blockIdx.y * ystride;
   float s = 0.f;
   if (c < N && out)
-    for (int p = threadIdx.y; p < P; p += 8) s += src[(size_t)p * pstride + c];
+    for (int p = threadIdx.y; p < P; p += 32) s += src[(size_t)p * pstride + c];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < N && out) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    for (int w = 0; w < 32; ++w) t += red[w][threadIdx.x];
     out[c] = accumulate ? out[c] + t : t;
   }
 }
@@ -291,22 +297,33 @@ __global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict
   }
 }
 // backward: dprompt[j,:] = sum_b q16?(g[b,row0+j,:]) in batch order; optionally zero those rows of g / g16.
+// block (32 columns, 8 batch groups): group y sums sequences y, y+8, ... in order; groups are combined in order
+// 0..7 (for N <= 8 this is the plain sequential batch order of autograd's expand-backward).
 __global__ void splice_bwd_kernel(float* __restrict__ g, bf16* __restrict__ g16, float* __restrict__ dprompt, int N,
                                   int T, int row0, int n_ctx, int D, int round16, int zero) {
+  __shared__ float red[8][33];
   const int j = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int b = 0; b < N; ++b) {
-    const size_t idx = ((size_t)b * T + row0 + j) * D + c;
-    const float v = g[idx];
-    s += round16 ? q16(v) : v;
-    if (zero) {
-      g[idx] = 0.f;
-      if (g16) g16[idx] = __float2bfloat16_rn(0.f);
+  if (c < D) {
+    for (int b = threadIdx.y; b < N; b += 8) {
+      const size_t idx = ((size_t)b * T + row0 + j) * D + c;
+      const float v = g[idx];
+      s += round16 ? q16(v) : v;
+      if (zero) {
+        g[idx] = 0.f;
+        if (g16) g16[idx] = __float2bfloat16_rn(0.f);
+      }
     }
   }
-  dprompt[(size_t)j * D + c] = s;
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    float t = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][threadIdx.x];
+    dprompt[(size_t)j * D + c] = t;
+  }
 }
 
 // g[rowidx[r], :] = dx[r, :] (+ bf16 copy); g must have been zero-filled.
@@ -382,20 +399,20 @@ __global__ void linear_small_bwd_w_kernel(const float* __restrict__ x, const flo
     db[n] = s;
   }
 }
-// block (32, 8): 32 consecutive k per block, 8 groups stride over n; fixed-order combine. grid (K/32, m).
+// block (32, 32): 32 consecutive k per block, 32 groups stride over n; fixed-order combine. grid (K/32, m).
 __global__ void linear_small_bwd_x_kernel(const float* __restrict__ W, const float* __restrict__ dy,
                                           const float* __restrict__ add, float* __restrict__ dx, int m, int N, int K) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int k = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y;
   float s = 0.f;
   if (k < K)
-    for (int n = threadIdx.y; n < N; n += 8) s += dy[(size_t)r * N + n] * W[(size_t)n * K + k];
+    for (int n = threadIdx.y; n < N; n += 32) s += dy[(size_t)r * N + n] * W[(size_t)n * K + k];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && k < K) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    for (int w = 0; w < 32; ++w) t += red[w][threadIdx.x];
     dx[(size_t)r * K + k] = t + (add ? add[(size_t)r * K + k] : 0.f);
   }
 }
@@ -412,9 +429,9 @@ extern "C" int mfk_layernorm_fwd(const float* x, const int* rowidx, const float*
   if (!y_bf16 && !y_f32) return MFK_EARG;
   const int grid = (M + kLnWarps - 1) / kLnWarps;
   bf16* y16 = static_cast<bf16*>(y_bf16);
-  if (D == 768) ln_fwd_kernel<6><<<grid, kLnWarps * 32, 0, ST(stream)>>>(x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
-  else if (D == 512) ln_fwd_kernel<4><<<grid, kLnWarps * 32, 0, ST(stream)>>>(x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
-  else if (D == 128) ln_fwd_kernel<1><<<grid, kLnWarps * 32, 0, ST(stream)>>>(x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  if (D == 768) launch_pdl(ln_fwd_kernel<6>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  else if (D == 512) launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  else if (D == 128) launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
   else return MFK_ESHAPE;
   MFK_CHECK_LAUNCH();
   return MFK_OK;
@@ -422,7 +439,7 @@ extern "C" int mfk_layernorm_fwd(const float* x, const int* rowidx, const float*
 
 extern "C" int mfk_ln_bwd_ctas(int M) {
   int g = (M + kLnWarps - 1) / kLnWarps;
-  return g < 592 ? g : 592;  // 4 CTAs per SM on 148 SMs (2 resident at a time)
+  return g < 296 ? g : 296;  // 2 resident CTAs per SM on 148 SMs
 }
 
 extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
@@ -436,8 +453,8 @@ extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
   float* part = (dgamma || dbeta) ? partial_ws : nullptr;
 #define LNB(V)                                                                                                     \
   do {                                                                                                             \
-    if (dy_is_bf16) ln_bwd_kernel<V, true><<<grid, kLnWarps * 32, 0, ST(stream)>>>(dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M); \
-    else ln_bwd_kernel<V, false><<<grid, kLnWarps * 32, 0, ST(stream)>>>(dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M);           \
+    if (dy_is_bf16) launch_pdl(ln_bwd_kernel<V, true>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M); \
+    else launch_pdl(ln_bwd_kernel<V, false>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M);           \
   } while (0)
   if (D == 768) LNB(6);
   else if (D == 512) LNB(4);
@@ -446,8 +463,8 @@ extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
 #undef LNB
   MFK_CHECK_LAUNCH();
   if (part) {
-    partial_reduce_kernel<<<dim3((D + 31) / 32, 2), dim3(32, 8), 0, ST(stream)>>>(part, grid, D, 2LL * D, D, dgamma,
-                                                                                  dbeta, accumulate);
+    launch_pdl(partial_reduce_kernel, dim3((D + 31) / 32, 2), dim3(32, 32), 0, ST(stream), (const float*)part, grid, D,
+               2LL * D, (long long)D, dgamma, dbeta, accumulate);
     MFK_CHECK_LAUNCH();
   }
   return MFK_OK;
@@ -460,7 +477,7 @@ extern "C" int mfk_colsum(const void* x, int is_bf16, long long ld, int M, int N
   dim3 grid((N + 63) / 64, P), block(32, 8);
   if (is_bf16) colsum_partial_kernel<true><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
   else colsum_partial_kernel<false><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
-  partial_reduce_kernel<<<dim3((N + 31) / 32, 1), dim3(32, 8), 0, ST(stream)>>>(partial_ws, P, N, N, 0, out, nullptr,
+  partial_reduce_kernel<<<dim3((N + 31) / 32, 1), dim3(32, 32), 0, ST(stream)>>>(partial_ws, P, N, N, 0, out, nullptr,
                                                                                 accumulate);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
@@ -504,8 +521,8 @@ extern "C" int mfk_prompt_splice_fwd(float* x, const float* prompt, int N, int T
 extern "C" int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int N, int T, int row0, int n_ctx, int D,
                                      int round_fp16, int zero_rows, void* stream) {
   if (!g || !dprompt || row0 < 0 || row0 + n_ctx > T) return MFK_EARG;
-  dim3 grid((D + 127) / 128, n_ctx);
-  splice_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(g, static_cast<bf16*>(g_bf16), dprompt, N, T, row0, n_ctx, D,
+  dim3 grid((D + 31) / 32, n_ctx);
+  splice_bwd_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(g, static_cast<bf16*>(g_bf16), dprompt, N, T, row0, n_ctx, D,
                                                   round_fp16, zero_rows);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
@@ -551,7 +568,7 @@ extern "C" int mfk_linear_small_bwd(const float* x, const float* W, const float*
                                     const float* dx_add, float* dx, int m, int N, int K, void* stream) {
   if (!x || !W || !dy || m <= 0) return MFK_EARG;
   if (dW) linear_small_bwd_w_kernel<<<N, 128, 0, ST(stream)>>>(x, dy, dW, db, m, N, K);
-  if (dx) linear_small_bwd_x_kernel<<<dim3((K + 31) / 32, m), dim3(32, 8), 0, ST(stream)>>>(W, dy, dx_add, dx, m, N, K);
+  if (dx) linear_small_bwd_x_kernel<<<dim3((K + 31) / 32, m), dim3(32, 32), 0, ST(stream)>>>(W, dy, dx_add, dx, m, N, K);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

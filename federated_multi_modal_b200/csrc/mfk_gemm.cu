@@ -118,6 +118,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel (PDL); from here on global memory is touched
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -410,8 +413,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  gemm_bf16_tn_kernel<BN, kStages, kMN><<<grid, kThreads, smem, st>>>(tmA, tmB, tmO32, tmO16, tmPre, p);
-  MFK_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BN, kStages, kMN>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB,
+                              tmO32, tmO16, tmPre, p);
+  if (le != cudaSuccess) return (int)le;
   return MFK_OK;
 }
 

@@ -62,6 +62,10 @@ int mfk_attn_bwd(const void* qkv, const void* out, const void* d_out, const floa
                  void* dqkv, int N, int T, int heads, int causal, void* stream);
 int mfk_attn_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
                     void* dqkv, int N, int T, int heads, int causal, void* stream);
+/* Non-causal backward with Q, K, V, dO of a (sequence, head) resident in smem and S / dP computed once per
+ * 128x128 block (five UMMA GEMMs per block, accumulators in TMEM) — the vision-tower path.           */
+int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
+                       void* dqkv, int N, int T, int heads, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm (clip/model.py:153-159)
  * fp32 statistics, eps as given (1e-5), D in {128, 512, 768}. rowidx (int32[M], may be NULL) gathers

@@ -111,13 +111,15 @@ def _attn_ref(qkv, N, T, heads, causal):
 @pytest.mark.parametrize("N,T,heads,causal", [(2, 199, 12, False), (3, 77, 8, True), (4, 16, 8, True),
                                               (2, 64, 2, False), (1, 256, 1, True), (5, 11, 8, True),
                                               (32, 199, 12, False)])
-@pytest.mark.parametrize("impl", ["mma", "tc"])
+@pytest.mark.parametrize("impl", ["mma", "tc", "fused"])
 def test_attention_fwd_bwd(N, T, heads, causal, impl):
+    if impl == "fused" and causal:
+        pytest.skip("the fused backward is the non-causal (vision) path")
     D = heads * 64
     qkv = rnd(N * T, 3 * D, dtype=BF16, seed=9)
     out = torch.empty(N * T, D, device=DEV, dtype=BF16)
     lse = torch.empty(N, heads, T, device=DEV, dtype=F32)
-    ops.attn_fwd(qkv, out, lse, N, T, heads, causal, impl=impl)
+    ops.attn_fwd(qkv, out, lse, N, T, heads, causal, impl="tc" if impl == "fused" else impl)
     x = qkv.float().requires_grad_(True)
     o_ref, p, _ = _attn_ref(x, N, T, heads, causal)
     assert (out.float() - o_ref).abs().max().item() < 2e-2

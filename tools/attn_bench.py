@@ -23,7 +23,7 @@ def timeit(fn):
         ts.append(s.elapsed_time(e) * 1e3)
     ts.sort(); return ts[len(ts) // 2]
 unit = 2.0 * T * T * 64 * N * H  # one T x T x 64 GEMM over all (sequence, head) pairs
-for impl in ("mma", "tc"):
-    f = timeit(lambda: ops.attn_fwd(qkv, out, lse, N, T, H, False, impl=impl))
+for impl in ("mma", "tc", "fused"):
+    f = timeit(lambda: ops.attn_fwd(qkv, out, lse, N, T, H, False, impl="tc" if impl == "fused" else impl))
     b = timeit(lambda: ops.attn_bwd(qkv, out, do, lse, delta, dqkv, N, T, H, False, impl=impl))
     print(f"{impl}: fwd {f:7.1f} us ({2 * unit / f / 1e6:6.1f} TFLOP/s algorithmic)   bwd {b:7.1f} us ({5 * unit / b / 1e6:6.1f} TFLOP/s algorithmic)")
