@@ -70,7 +70,9 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0,
 
 // kMN = false: A[M,K], B[N,K] (K contiguous; "TN").  kMN = true: A given as [K,M], B as [K,N] (M / N contiguous:
 // MN-major UMMA operands) — the wgrad form dW = dY^T X straight from the row-major activations, no transposes.
-template <int BN, int kStages, bool kMN>
+// EPI selects the epilogue at compile time (keeps each variant's register footprint small):
+//   0 plain (+bias)   1 bias + QuickGELU (+pre-activation store)   2 * QuickGELU'(aux)   3 (+bias) + fp32 residual
+template <int BN, int kStages, bool kMN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -197,6 +199,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t row128 = sbuf_u32 + lane * 128, x128 = lane & 7;            // 128-B rows, SWIZZLE_128B
     const uint32_t row64a = sbuf_u32 + lane * 64, x64 = (lane >> 1) & 3;       // 64-B rows,  SWIZZLE_64B
     const uint32_t row64b = row64a + 2048;                                     // second bf16 output
+    // Epilogue operands that do not depend on the accumulator (fp32 residual / QuickGELU aux) are fetched one
+    // chunk ahead — across tile boundaries too — so their DRAM latency hides behind the previous chunk.
+    float4 rv_nx[EPI == 3 ? 8 : 1];
+    uint4 av_nx[EPI == 2 ? 4 : 1];
+    auto fetch_ops = [&](int t, int c) {
+      if (t >= p.total_tiles) return;
+      int m0, n0, w;
+      decode_tile(p, t, m0, n0, w);
+      const int row = m0 + q * 32 + lane, col = n0 + c;
+      if (c >= w || row >= p.M || col >= p.N) return;
+      if (EPI == 3) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)row * p.ldres + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rv_nx[j] = r4[j];
+      }
+      if (EPI == 2) {
+        const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av_nx[j] = __ldg(a4 + j);
+      }
+    };
+    fetch_ops(blockIdx.x, half * 32);
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int m0, n0, w;
@@ -210,24 +234,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = half * 32; c < w; c += 64) {
         const int col = n0 + c;
         const bool ok = row_ok && col < p.N;
-        // ---- operands that do not depend on the accumulator: issue their loads first
-        float4 bv[8];
-        float4 rv[8];
-        uint4 av[4];
-        if (p.bias && col < p.N) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+        float4 rv[EPI == 3 ? 8 : 1];
+        uint4 av[EPI == 2 ? 4 : 1];
+        if (EPI == 3) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
+          for (int j = 0; j < 8; ++j) rv[j] = rv_nx[j];
         }
-        if (p.res && ok) {
-          const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)row * p.ldres + col);
+        if (EPI == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rv[j] = r4[j];
+          for (int j = 0; j < 4; ++j) av[j] = av_nx[j];
         }
-        if (p.act == 2 && ok) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) av[j] = __ldg(a4 + j);
+        if (EPI >= 2) {  // next chunk of this tile, else the first chunk of this CTA's next tile
+          if (c + 64 < w) fetch_ops(t, c + 64);
+          else fetch_ops(t + (int)gridDim.x, half * 32);
         }
         if (!waited) {
           mbar_wait(&tfull_bar[acc], acc_phase);
@@ -240,17 +259,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+        if (EPI != 2 && p.bias && col < p.N) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+            const float4 bv = __ldg(b4 + j);
+            v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
           }
         }
         // previous TMA stores of this warp must have finished READING the staging buffer
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        if (p.act == 1) {
-          if (p.outpre) {
+        const bool has_pre = EPI == 1 && p.outpre != nullptr;
+        if (EPI == 1) {
+          if (has_pre) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row64b + ((j ^ x64) << 4)),
@@ -261,26 +283,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // the activation is applied to the bf16-rounded pre-activation that backward will re-read
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = quickgelu(__bfloat162float(__float2bfloat16_rn(v[j])));
-        } else if (p.act == 2) {
-          if (ok) {
+        }
+        if (EPI == 2 && ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 u0 = unpack_bf16(av[j].x), u1 = unpack_bf16(av[j].y), u2 = unpack_bf16(av[j].z),
-                     u3 = unpack_bf16(av[j].w);
-              v[8 * j] *= dquickgelu(u0.x); v[8 * j + 1] *= dquickgelu(u0.y);
-              v[8 * j + 2] *= dquickgelu(u1.x); v[8 * j + 3] *= dquickgelu(u1.y);
-              v[8 * j + 4] *= dquickgelu(u2.x); v[8 * j + 5] *= dquickgelu(u2.y);
-              v[8 * j + 6] *= dquickgelu(u3.x); v[8 * j + 7] *= dquickgelu(u3.y);
-            }
+          for (int j = 0; j < 4; ++j) {
+            float2 u0 = unpack_bf16(av[j].x), u1 = unpack_bf16(av[j].y), u2 = unpack_bf16(av[j].z),
+                   u3 = unpack_bf16(av[j].w);
+            v[8 * j] *= dquickgelu(u0.x); v[8 * j + 1] *= dquickgelu(u0.y);
+            v[8 * j + 2] *= dquickgelu(u1.x); v[8 * j + 3] *= dquickgelu(u1.y);
+            v[8 * j + 4] *= dquickgelu(u2.x); v[8 * j + 5] *= dquickgelu(u2.y);
+            v[8 * j + 6] *= dquickgelu(u3.x); v[8 * j + 7] *= dquickgelu(u3.y);
           }
         }
-        if (p.res && ok) {
+        if (EPI == 3 && ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w;
           }
         }
-        const bool has_pre = p.act == 1 && p.outpre != nullptr;
         if (p.out16 || has_pre) {
           if (p.out16) {
 #pragma unroll
@@ -401,19 +421,19 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int kStages, bool kMN>
+template <int BN, int kStages, bool kMN, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO32,
                        const CUtensorMap& tmO16, const CUtensorMap& tmPre, const GemmParams& p, int grid,
                        cudaStream_t st) {
   static bool configured = false;
   constexpr size_t smem = gemm_smem_bytes<BN, kStages>();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages, kMN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages, kMN, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BN, kStages, kMN>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB,
+  cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BN, kStages, kMN, EPI>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB,
                               tmO32, tmO16, tmPre, p);
   if (le != cudaSuccess) return (int)le;
   return MFK_OK;
@@ -473,8 +493,17 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
     return rc;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256, 4, false>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
-  return launch_gemm<128, 6, false>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+  const int epi = act == 1 ? 1 : act == 2 ? 2 : residual ? 3 : 0;
+#define MFK_GEMM_DISPATCH(BN_, ST_)                                                                           \
+  switch (epi) {                                                                                              \
+    case 0: return launch_gemm<BN_, ST_, false, 0>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);               \
+    case 1: return launch_gemm<BN_, ST_, false, 1>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);               \
+    case 2: return launch_gemm<BN_, ST_, false, 2>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);               \
+    default: return launch_gemm<BN_, ST_, false, 3>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);              \
+  }
+  if (bn == 256) { MFK_GEMM_DISPATCH(256, 4) }
+  MFK_GEMM_DISPATCH(128, 6)
+#undef MFK_GEMM_DISPATCH
 }
 
 // out[M,N] (fp32) = At^T * Bt with At[K,M], Bt[K,N] bf16 row-major (leading dimensions lda, ldb >= M, N).
@@ -504,5 +533,5 @@ extern "C" int mfk_gemm_bf16_at_b(const void* At, long long lda, const void* Bt,
   if ((rc = mfk_make_tmap_2d(&tmO32, out_f32, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ld32, 32, 32, 128)) != MFK_OK)
     return rc;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  return launch_gemm<256, 4, true>(tmA, tmB, tmO32, tmA, tmA, p, grid, static_cast<cudaStream_t>(stream));
+  return launch_gemm<256, 4, true, 0>(tmA, tmB, tmO32, tmA, tmA, p, grid, static_cast<cudaStream_t>(stream));
 }

@@ -7,6 +7,8 @@ from federated_multi_modal_b200 import ops
 dev = "cuda"
 BF16, F32 = torch.bfloat16, torch.float32
 M = int(os.environ.get("GB_M", 6368))
+TN = int(os.environ.get("GB_TILE_N", 0))
+CUBLAS = int(os.environ.get("GB_CUBLAS", 1))
 SHAPES = [  # name, M, N, K, epilogue
     ("qkv_fwd", M, 2304, 768, "bias16"),
     ("out_fwd", M, 768, 768, "bias_res32"),
@@ -34,12 +36,12 @@ for name, m, n, k, epi in SHAPES:
     o32 = torch.empty(m, n, device=dev)
     aux = torch.randn(m, n, device=dev).to(BF16)
     def run():
-        if epi == "bias16": ops.gemm(a, b, bias=bias, out_bf16=o16, k=k)
-        elif epi == "plain16": ops.gemm(a, b, out_bf16=o16, k=k)
-        elif epi == "plain32": ops.gemm(a, b, out_f32=o32, k=k)
-        elif epi == "bias_res32": ops.gemm(a, b, bias=bias, residual=resid, out_f32=o32, k=k)
-        elif epi == "gelu": ops.gemm(a, b, bias=bias, act=1, out_bf16=o16, out_pre=o16b, k=k)
-        elif epi == "dgelu": ops.gemm(a, b, act=2, aux=aux, out_bf16=o16, k=k)
+        if epi == "bias16": ops.gemm(a, b, bias=bias, out_bf16=o16, k=k, tile_n=TN)
+        elif epi == "plain16": ops.gemm(a, b, out_bf16=o16, k=k, tile_n=TN)
+        elif epi == "plain32": ops.gemm(a, b, out_f32=o32, k=k, tile_n=TN)
+        elif epi == "bias_res32": ops.gemm(a, b, bias=bias, residual=resid, out_f32=o32, k=k, tile_n=TN)
+        elif epi == "gelu": ops.gemm(a, b, bias=bias, act=1, out_bf16=o16, out_pre=o16b, k=k, tile_n=TN)
+        elif epi == "dgelu": ops.gemm(a, b, act=2, aux=aux, out_bf16=o16, k=k, tile_n=TN)
     for _ in range(3): run()
     ts = []
     for _ in range(10):
@@ -51,8 +53,8 @@ for name, m, n, k, epi in SHAPES:
     t = ts[len(ts) // 2]
     tf = 2.0 * m * n * k / t / 1e6
     # cuBLAS reference point (library call, for context only)
-    tt = []
-    for _ in range(5):
+    tt = [0.0]
+    for _ in range(5 if CUBLAS else 0):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); torch.matmul(a[:, :k], b[:, :k].t()); e.record(); torch.cuda.synchronize()
