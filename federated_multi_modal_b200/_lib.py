@@ -39,6 +39,7 @@ SIGNATURES = {
     "mfk_scatter_rows": [P, P, P, P, I, I, P],
     "mfk_transpose_bf16": [P, I, L, P, L, P, L, I, I, P],
     "mfk_cast_f32_bf16": [P, P, L, P],
+    "mfk_split_bf16x3": [P, P, I, I, P],
     "mfk_linear_small_fwd": [P, P, P, P, I, I, I, P],
     "mfk_linear_small_bwd": [P, P, P, P, P, P, P, I, I, I, P],
     "mfk_head_workspace_floats": [I, I, I],

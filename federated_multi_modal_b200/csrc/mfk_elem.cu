@@ -370,6 +370,22 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
   }
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): out[r] = [hi | lo | hi] (K-concatenated A operand). Against a
+// weight packed as [hi | hi | lo] one bf16 GEMM of depth 3K yields hi*hi + lo*hi + hi*lo, i.e. ~16 mantissa bits —
+// used for the two feature heads, whose rounding error would otherwise dominate the logit error.
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * D) return;
+  const int r = (int)(i / D), c = (int)(i % D);
+  const float v = x[i];
+  const bf16 hi = __float2bfloat16_rn(v);
+  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = out + (size_t)r * 3 * D;
+  o[c] = hi;
+  o[D + c] = lo;
+  o[2 * D + c] = hi;
+}
+
 // ============================================================================ small fp32 linears (prompt learner)
 // trainers/maple.py:194-215: y[m,N] = x[m,K] W[N,K]^T + b, m = n_ctx (tiny). One warp per output column.
 __global__ void linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
@@ -552,6 +568,14 @@ extern "C" int mfk_cast_f32_bf16(const float* in, void* out, long long n, void* 
   if (!in || !out || n <= 0) return MFK_EARG;
   const long long thr = (n + 3) / 4;
   cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, ST(stream)>>>(in, static_cast<bf16*>(out), n);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_split_bf16x3(const float* x, void* out_bf16, int rows, int D, void* stream) {
+  if (!x || !out_bf16 || rows <= 0 || D <= 0) return MFK_EARG;
+  const long long n = (long long)rows * D;
+  split_bf16x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, static_cast<bf16*>(out_bf16), rows, D);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

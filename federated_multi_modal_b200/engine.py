@@ -169,11 +169,19 @@ class MapleEngine:
         self.vpos = f32(v + "positional_embedding")
         proj = sd[v + "proj"].to(dev, F32)
         self.vproj = proj.to(BF16).contiguous()          # [768,512]  (B operand of the dgrad GEMM)
-        self.vproj_T = proj.t().to(BF16).contiguous()    # [512,768]  (B operand of the forward GEMM)
+        self.vproj_T = self._split_b(proj.t())           # [512,3*768] hi|hi|lo (B operand of the forward GEMM)
         self.tpos = f32(t + "positional_embedding")
         tp = sd[t + "text_projection"].to(dev, F32)
         self.tproj = tp.to(BF16).contiguous()
-        self.tproj_T = tp.t().to(BF16).contiguous()
+        self.tproj_T = self._split_b(tp.t())
+
+    @staticmethod
+    def _split_b(w: torch.Tensor) -> torch.Tensor:
+        """[N,K] fp32 -> bf16 [N,3K] = hi | hi | lo (pairs with ops.split_bf16x3's hi | lo | hi A operand)."""
+        w = w.contiguous().float()
+        hi = w.to(BF16)
+        lo = (w - hi.float()).to(BF16)
+        return torch.cat([hi, hi, lo], dim=1).contiguous()
 
     def repack_trainable(self):
         """Refresh the bf16 (and transposed) copies of the trainable resblock weights from the fp32 arena."""
@@ -340,12 +348,15 @@ class MapleEngine:
         self.vx0 = x0
 
     def _features(self, tw: _Tower, xout, rows, ln_g, ln_b, projT, name, R, train):
-        y = self._buf(name + ".y", (R, tw.D), BF16)
+        y = self._buf(name + ".y", (R, tw.D), F32)
+        y3 = self._buf(name + ".y3", (R, 3 * tw.D), BF16)
         xs = self._buf(name + ".xs", (R, tw.D), F32)
         stat = self._buf(name + ".st", (2, R), F32)
-        ops.layernorm_fwd(xout, ln_g, ln_b, rowidx=rows, y_bf16=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
+        ops.layernorm_fwd(xout, ln_g, ln_b, rowidx=rows, y_f32=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
+        # split-precision head (hi/lo bf16, one GEMM of depth 3D): keeps ~16 mantissa bits in the features
+        ops.split_bf16x3(y, y3)
         feat = self._buf(name + ".feat", (R, self.E), F32)
-        ops.gemm(y, projT, out_f32=feat)
+        ops.gemm(y3, projT, out_f32=feat)
         return feat, xs, stat
 
     def _text_features(self, train: bool):

@@ -126,6 +126,10 @@ def cast_bf16(inp, out):
     call("mfk_cast_f32_bf16", inp, out, inp.numel(), stream_ptr())
 
 
+def split_bf16x3(x, out):
+    call("mfk_split_bf16x3", x, out, x.shape[0], x.shape[1], stream_ptr())
+
+
 def linear_small_fwd(x, W, b, y):
     call("mfk_linear_small_fwd", x, W, b, y, x.shape[0], W.shape[0], W.shape[1], stream_ptr())
 

@@ -108,6 +108,10 @@ int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16,
 int mfk_transpose_bf16(const void* in, int in_is_f32, long long ldi, void* out, long long ldo, void* copy,
                        long long ldc, int M, int N, void* stream);
 int mfk_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* out[rows, 3D] bf16 = [hi | lo | hi] with x = hi + lo: K-concatenated A operand of a split-precision GEMM whose
+ * B operand is packed [hi | hi | lo]; one mfk_gemm_bf16 of depth 3D then carries ~16 mantissa bits. Used for the
+ * feature heads (`x @ proj`, clip/model.py:569-570; `@ text_projection`, trainers/maple.py:76).        */
+int mfk_split_bf16x3(const float* x, void* out_bf16, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------ prompt-learner projections (fp32)
  * y[m,N] = x[m,K] W[N,K]^T + b (trainers/maple.py:194-215; m = n_ctx) and its backward.               */
