@@ -359,14 +359,19 @@ class MapleEngine:
         ops.gemm(y3, projT, out_f32=feat)
         return feat, xs, stat
 
-    def _text_features(self, train: bool):
+    def _text_features(self, train: bool, class_range=None):
+        """Text tower over all classes, or over the contiguous class shard [c0, c1) (inference, config 5)."""
         tw, p = self.txt, self.p
-        self._tower_bufs(tw, self.C, self.Te, train)
-        ops.text_assemble(self.prefix, p["prompt_learner.ctx"], self.suffix, self.tpos, tw.ws["x1"][0], self.C,
-                          self.Te, self.n, self.Tfull)
+        c0, c1 = (0, self.C) if class_range is None else class_range
+        Cn = c1 - c0
+        self._tower_bufs(tw, Cn, self.Te, train)
+        ops.text_assemble(self.prefix[c0:c1], p["prompt_learner.ctx"], self.suffix[c0:c1], self.tpos,
+                          tw.ws["x1"][0], Cn, self.Te, self.n, self.Tfull)
         xout = self._tower_fwd(tw, self.deep_text, 1, train)
-        return self._features(tw, xout, self.eot_rows, p["text_encoder.ln_final.weight"],
-                              p["text_encoder.ln_final.bias"], self.tproj_T, "txt", self.C, train)
+        rows = self.eot_rows if class_range is None else \
+            (self.eot_rows[c0:c1] - c0 * self.Te).contiguous()
+        return self._features(tw, xout, rows, p["text_encoder.ln_final.weight"],
+                              p["text_encoder.ln_final.bias"], self.tproj_T, "txt", Cn, train)
 
     def _image_features(self, img, train: bool):
         tw, p = self.vis, self.p
@@ -382,15 +387,28 @@ class MapleEngine:
 
     # ------------------------------------------------------------------ public: inference
     @torch.no_grad()
-    def logits(self, img: torch.Tensor, cache_text: bool = True) -> torch.Tensor:
+    def logits(self, img: torch.Tensor, cache_text: bool = True, shard_classes: bool = False) -> torch.Tensor:
         """Eval path of CustomCLIP.forward (trainers/maple.py:381): returns logits [B, C] (fp32).
-        Text features are input independent and cached across eval batches until parameters change."""
+        Text features are input independent and cached across eval batches until parameters change.
+        ``shard_classes``: under torch.distributed each rank runs the text tower on C/world classes and the
+        [C, E] feature matrix is all-gathered once; images stay data-parallel."""
         img = img.to(self.dev, F32).contiguous()
         B = img.shape[0]
         self._prompt_learner_fwd()
         if not (cache_text and self._text_cache_valid):
-            ft, _, _ = self._text_features(False)
-            self._ft_cache = ft.clone()
+            import torch.distributed as dist
+            if shard_classes and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                world, rank = dist.get_world_size(), dist.get_rank()
+                if self.C % world:
+                    raise ValueError(f"shard_classes needs C={self.C} divisible by world size {world}")
+                per = self.C // world
+                ft, _, _ = self._text_features(False, (rank * per, (rank + 1) * per))
+                full = torch.empty(self.C, self.E, device=self.dev, dtype=F32)
+                dist.all_gather_into_tensor(full, ft.contiguous())
+                self._ft_cache = full
+            else:
+                ft, _, _ = self._text_features(False)
+                self._ft_cache = ft.clone()
             self._text_cache_valid = True
         fi, _, _ = self._image_features(img, False)
         out = torch.empty(B, self.C, device=self.dev, dtype=F32)

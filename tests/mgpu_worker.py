@@ -73,6 +73,18 @@ def main():
         else:
             ex.status.cpu()
         dist.barrier()
+    if backend == "nccl":
+        # config 5: classes sharded over ranks for the text tower, features all-gathered once
+        from helpers import customclip_state_dict
+        from federated_multi_modal_b200 import synth
+        from federated_multi_modal_b200.engine import MapleEngine
+        C = 16 * world
+        sd, tok = customclip_state_dict(C, layers=2)
+        eng = MapleEngine(sd, tok, device=str(dev))
+        img, _ = synth.make_batch(2, C, 11 + rank)
+        a = eng.logits(img.to(dev), cache_text=False, shard_classes=True)
+        b = eng.logits(img.to(dev), cache_text=False, shard_classes=False)
+        assert torch.equal(a, b), (a - b).abs().max()
     if rank == 0:
         print(f"MGPU_OK backend={backend} world={world} transport={ex.transport}")
     dist.barrier()
