@@ -338,6 +338,21 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dx, const int* __r
   }
 }
 
+// dst[r, :] = src[rowidx[r], :] in 16-byte chunks (row_bytes % 16 == 0)
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ rowidx,
+                                   uint4* __restrict__ dst, int chunks_per_row) {
+  const int r = blockIdx.x;
+  const size_t s0 = (size_t)rowidx[r] * chunks_per_row, d0 = (size_t)r * chunks_per_row;
+  for (int i = threadIdx.x; i < chunks_per_row; i += blockDim.x) dst[d0 + i] = src[s0 + i];
+}
+// dst[rowidx[r], :] = src[r, :] (bf16 rows); dst must have been zero-filled
+__global__ void scatter_rows_bf16_kernel(const uint4* __restrict__ src, const int* __restrict__ rowidx,
+                                         uint4* __restrict__ dst, int chunks_per_row) {
+  const int r = blockIdx.x;
+  const size_t d0 = (size_t)rowidx[r] * chunks_per_row, s0 = (size_t)r * chunks_per_row;
+  for (int i = threadIdx.x; i < chunks_per_row; i += blockDim.x) dst[d0 + i] = src[s0 + i];
+}
+
 // ============================================================================ transposes / packing
 template <typename TIN>
 __global__ void transpose_to_bf16_kernel(const TIN* __restrict__ in, long long ldi, bf16* __restrict__ out,
@@ -548,6 +563,18 @@ extern "C" int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, vo
                                 void* stream) {
   if (!dx || !rowidx || !g || R <= 0) return MFK_EARG;
   scatter_rows_kernel<<<R, 128, 0, ST(stream)>>>(dx, rowidx, g, static_cast<bf16*>(g_bf16), D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_gather_rows(const void* src, const int* rowidx, void* dst, int R, long long row_bytes, int scatter,
+                               void* stream) {
+  if (!src || !rowidx || !dst || R <= 0 || row_bytes <= 0 || row_bytes % 16) return MFK_EARG;
+  const int chunks = (int)(row_bytes / 16);
+  if (scatter)
+    scatter_rows_bf16_kernel<<<R, 128, 0, ST(stream)>>>(static_cast<const uint4*>(src), rowidx, static_cast<uint4*>(dst), chunks);
+  else
+    gather_rows_kernel<<<R, 128, 0, ST(stream)>>>(static_cast<const uint4*>(src), rowidx, static_cast<uint4*>(dst), chunks);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

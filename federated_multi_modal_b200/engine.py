@@ -224,6 +224,21 @@ class MapleEngine:
         ws["qkv"] = b("qkv", (nl, M, 3 * D), BF16)
         ws["att"] = b("att", (nl, M, D), BF16)
         ws["act"] = b("act", (M, 4 * D), BF16)
+        # last block: only one row per sequence (CLS / EOT) is consumed -> out-proj + MLP on N gathered rows
+        R = N
+        ws["att_r"] = b("att_r", (R, D), BF16)
+        ws["x1_r"] = b("x1_r", (R, D), F32)
+        ws["x2_r"] = b("x2_r", (R, D), F32)
+        ws["h2_r"] = b("h2_r", (R, D), BF16)
+        ws["act_r"] = b("act_r", (R, 4 * D), BF16)
+        ws["xout_r"] = b("xout_r", (R, D), F32)
+        if train:
+            ws["u_r"] = b("u_r", (R, 4 * D), BF16)
+            ws["stat_r"] = b("stat_r", (2, R), F32)
+            ws["g_r"] = b("g_r", (R, D), F32)
+            ws["g16_r"] = b("g16_r", (R, D), BF16)
+            ws["du_r"] = b("du_r", (R, 4 * D), BF16)
+            ws["dh_r"] = b("dh_r", (R, D), BF16)
         if train:
             ws["u"] = b("u", (L, M, 4 * D), BF16)
             ws["lse"] = b("lse", (L, N * tw.heads * T), F32)
@@ -266,7 +281,9 @@ class MapleEngine:
         """(x1 in, x1 out, per-layer slot) — training keeps every layer, inference ping-pongs two buffers."""
         return (l, l + 1, l) if train else (l % 2, (l + 1) % 2, 0)
 
-    def _block_fwd(self, tw: _Tower, l: int, train: bool):
+    def _block_fwd(self, tw: _Tower, l: int, train: bool, rows=None):
+        """rows (int32 [N]) is given for the LAST block only: everything after the attention core then runs on
+        those gathered rows and the compact [N, D] result is returned."""
         ws, w = tw.ws, tw.w[l]
         si, so, s = self._slots(l, train)
         x1, x1n, x2 = ws["x1"][si], ws["x1"][so], ws["x2"][s]
@@ -275,6 +292,18 @@ class MapleEngine:
         qkv, att = ws["qkv"][s], ws["att"][s]
         ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=qkv)
         ops.attn_fwd(qkv, att, ws["lse"][l] if train else None, tw.N, tw.T, tw.heads, tw.causal)
+        if rows is not None:
+            sr = ws["stat_r"] if train else (None, None)
+            ops.gather_rows(att, rows, ws["att_r"])
+            ops.gather_rows(x1, rows, ws["x1_r"])
+            ops.gemm(ws["att_r"], w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=ws["x1_r"],
+                     out_f32=ws["x2_r"])
+            ops.layernorm_fwd(ws["x2_r"], w["ln_2.g"], w["ln_2.b"], y_bf16=ws["h2_r"], mean=sr[0], rstd=sr[1])
+            ops.gemm(ws["h2_r"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act_r"],
+                     out_pre=ws["u_r"] if train else None)
+            ops.gemm(ws["act_r"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=ws["x2_r"],
+                     out_f32=ws["xout_r"])
+            return ws["xout_r"]
         ops.gemm(att, w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=x1, out_f32=x2)
         ops.layernorm_fwd(x2, w["ln_2.g"], w["ln_2.b"], y_bf16=ws["h2"], mean=st[2], rstd=st[3])
         ops.gemm(ws["h2"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act"],
@@ -282,19 +311,50 @@ class MapleEngine:
         ops.gemm(ws["act"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=x2, out_f32=x1n)
         return x1n
 
-    def _tower_fwd(self, tw: _Tower, deep: List[torch.Tensor], row0: int, train: bool):
+    def _tower_fwd(self, tw: _Tower, deep: List[torch.Tensor], row0: int, train: bool, rows=None):
+        """Returns the compact [N, D] output rows (CLS / EOT) of the last block."""
         out = None
         for l in range(tw.L):
             if l >= 1 and (l - 1) < len(deep):
                 ops.prompt_splice_fwd(tw.ws["x1"][self._slots(l, train)[0]], deep[l - 1], tw.N, tw.T, row0, self.n)
-            out = self._block_fwd(tw, l, train)
+            out = self._block_fwd(tw, l, train, rows if l == tw.L - 1 else None)
         return out
 
     def _wgrad(self, tw: _Tower, dy16, x16, dW, Nout, Kin):
         """dW[Nout,Kin] = dy^T x straight from the row-major bf16 activations (MN-major UMMA operands)."""
         ops.gemm_at_b(dy16, x16, dW)
 
-    def _block_bwd(self, tw: _Tower, l: int):
+    def _last_block_bwd_rows(self, tw: _Tower, rows):
+        """Backward of the last block's out-proj + MLP on the gathered rows. In: ws["g_r"] / ws["g16_r"] = gradient
+        at the block output rows. Out: ws["g"] / ws["g16"] (full, zero except `rows`) = gradient after the attention
+        residual, ws["dh"] (full bf16, zero except `rows`) = gradient wrt the attention output."""
+        l = tw.L - 1
+        ws, w, D = tw.ws, tw.w[l], tw.D
+        pre = f"{tw.name}.transformer.resblocks.{l}."
+        wg, ln_grads, G = self.wgrad_last, self.trainable == "reference", self.g
+        g, g16 = ws["g_r"], ws["g16_r"]
+        ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u_r"], out_bf16=ws["du_r"])
+        if wg:
+            ops.gemm_at_b(g16, ws["act_r"], G[pre + "mlp.c_proj.weight"])
+            ops.colsum(g, G[pre + "mlp.c_proj.bias"], ws["csum"])
+        ops.gemm(ws["du_r"], w["mlp.c_fc.wT"], out_bf16=ws["dh_r"])
+        if wg:
+            ops.gemm_at_b(ws["du_r"], ws["h2_r"], G[pre + "mlp.c_fc.weight"])
+            ops.colsum(ws["du_r"], G[pre + "mlp.c_fc.bias"], ws["csum"])
+        sr = ws["stat_r"]
+        ops.layernorm_bwd(ws["dh_r"], ws["x2_r"], sr[0], sr[1], w["ln_2.g"], g_in=g, g_out=g, g_out_bf16=g16,
+                          dgamma=G[pre + "ln_2.weight"] if ln_grads else None,
+                          dbeta=G[pre + "ln_2.bias"] if ln_grads else None, partial_ws=ws["lnp"], M=g.shape[0])
+        ops.gemm(g16, w["attn.out_proj.wT"], out_bf16=ws["dh_r"])
+        if wg:
+            ops.gemm_at_b(g16, ws["att_r"], G[pre + "attn.out_proj.weight"])
+            ops.colsum(g, G[pre + "attn.out_proj.bias"], ws["csum"])
+        ws["g"].zero_(); ws["g16"].zero_(); ws["dh"].zero_()
+        ops.scatter_rows(g, rows, ws["g"], ws["g16"])
+        ops.gather_rows(ws["dh_r"], rows, ws["dh"], scatter=True)
+
+    def _block_bwd(self, tw: _Tower, l: int, attn_only: bool = False):
+        """attn_only: the MLP / out-proj part was already done on gathered rows (_last_block_bwd_rows)."""
         ws, w, D, M = tw.ws, tw.w[l], tw.D, tw.M
         g, g16 = ws["g"], ws["g16"]
         st = ws["stat"][l]
@@ -302,6 +362,18 @@ class MapleEngine:
         wg = self.wgrad_last and l == tw.L - 1
         ln_grads = self.trainable == "reference"
         G = self.g
+        if attn_only:
+            da = ws["dh"]
+            ops.attn_bwd(ws["qkv"][l], ws["att"][l], da, ws["lse"][l], ws["delta"], ws["dqkv"], tw.N, tw.T, tw.heads,
+                         tw.causal)
+            ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"])
+            if wg:
+                self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)
+                ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
+            ops.layernorm_bwd(ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
+                              dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
+                              dbeta=G[pre + "ln_1.bias"] if ln_grads else None, partial_ws=ws["lnp"])
+            return
         # ---- MLP branch
         ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"])
         if wg:
@@ -352,7 +424,7 @@ class MapleEngine:
         y3 = self._buf(name + ".y3", (R, 3 * tw.D), BF16)
         xs = self._buf(name + ".xs", (R, tw.D), F32)
         stat = self._buf(name + ".st", (2, R), F32)
-        ops.layernorm_fwd(xout, ln_g, ln_b, rowidx=rows, y_f32=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
+        ops.layernorm_fwd(xout, ln_g, ln_b, y_f32=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
         # split-precision head (hi/lo bf16, one GEMM of depth 3D): keeps ~16 mantissa bits in the features
         ops.split_bf16x3(y, y3)
         feat = self._buf(name + ".feat", (R, self.E), F32)
@@ -367,21 +439,22 @@ class MapleEngine:
         self._tower_bufs(tw, Cn, self.Te, train)
         ops.text_assemble(self.prefix[c0:c1], p["prompt_learner.ctx"], self.suffix[c0:c1], self.tpos,
                           tw.ws["x1"][0], Cn, self.Te, self.n, self.Tfull)
-        xout = self._tower_fwd(tw, self.deep_text, 1, train)
         rows = self.eot_rows if class_range is None else \
             (self.eot_rows[c0:c1] - c0 * self.Te).contiguous()
+        self.txt_rows = rows
+        xout = self._tower_fwd(tw, self.deep_text, 1, train, rows)
         return self._features(tw, xout, rows, p["text_encoder.ln_final.weight"],
                               p["text_encoder.ln_final.bias"], self.tproj_T, "txt", Cn, train)
 
     def _image_features(self, img, train: bool):
         tw, p = self.vis, self.p
         self._vision_embed(img, train)
-        xout = self._tower_fwd(tw, self.deep_vis, self.Tv - self.n, train)
         B = img.shape[0]
         key = f"cls_rows{B}"
         if key not in self._bufs:
             self._bufs[key] = (torch.arange(B, device=self.dev, dtype=torch.int32) * self.Tv).contiguous()
         self.cls_rows = self._bufs[key]
+        xout = self._tower_fwd(tw, self.deep_vis, self.Tv - self.n, train, self.cls_rows)
         return self._features(tw, xout, self.cls_rows, p["image_encoder.ln_post.weight"],
                               p["image_encoder.ln_post.bias"], self.vproj_T, "vis", B, train)
 
@@ -436,16 +509,13 @@ class MapleEngine:
         ops.cast_bf16(dfeat, d16)
         dy = self._buf(tw.name + ".dy", (R, D), F32)
         ops.gemm(d16, proj, out_f32=dy)
-        dxr = self._buf(tw.name + ".dxr", (R, D), F32)
-        ops.layernorm_bwd(dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=dxr,
+        ops.layernorm_bwd(dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=ws["g_r"], g_out_bf16=ws["g16_r"],
                           dgamma=G[lnname + ".weight"] if ln_grads else None,
                           dbeta=G[lnname + ".bias"] if ln_grads else None, partial_ws=ws["lnp"], M=R)
-        ws["g"].zero_()
-        ws["g16"].zero_()
-        ops.scatter_rows(dxr, rows, ws["g"], ws["g16"])
+        self._last_block_bwd_rows(tw, rows)
         got = {}
         for l in reversed(range(tw.L)):
-            self._block_bwd(tw, l)
+            self._block_bwd(tw, l, attn_only=(l == tw.L - 1))
             if l >= 1 and (l - 1) < nd:
                 dp = self._buf(f"{tw.name}.dprompt{l - 1}", (n, D), F32)
                 ops.prompt_splice_bwd(ws["g"], ws["g16"], dp, tw.N, tw.T, deep_row0, n, True, True)
@@ -486,7 +556,7 @@ class MapleEngine:
 
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            dt = self._tower_bwd(self.txt, dft, self.tproj, txs, tstat, self.eot_rows, "text_encoder.ln_final", C, 1)
+            dt = self._tower_bwd(self.txt, dft, self.tproj, txs, tstat, self.txt_rows, "text_encoder.ln_final", C, 1)
             d_ctx_t = self._buf("pl.dctx_t", (n, self.txt.D), F32)
             ops.prompt_splice_bwd(self.txt.ws["g"], None, d_ctx_t, C, self.Te, 1, n, False, False)
         dv = self._tower_bwd(self.vis, dfi, self.vproj, vxs, vstat, self.cls_rows, "image_encoder.ln_post", B,
@@ -561,10 +631,12 @@ class MapleEngine:
     def flops_per_step(self, B: int) -> float:
         """Algorithmic FLOPs of one fwd+bwd step for the work actually performed."""
         def tower(D, L, T, N, causal, wg):
-            lin = 2 * N * T * D * (3 * D + D + 4 * D + 4 * D)            # per layer fwd
+            lin = 2 * N * T * D * (3 * D + D + 4 * D + 4 * D)            # one full layer, forward
             att = 4 * N * T * T * D * ((T + 1) / (2 * T) if causal else 1.0)
-            fwd = L * (lin + att)
-            bwd = L * (lin + 2 * att) + (lin if wg else 0)
+            # last layer: in-proj + attention on all rows, out-proj + MLP only on the N consumed rows
+            last = 2 * N * T * D * 3 * D + 2 * N * D * (D + 4 * D + 4 * D)
+            fwd = (L - 1) * (lin + att) + last + att
+            bwd = (L - 1) * (lin + 2 * att) + last + 2 * att + (last if wg else 0)
             return fwd, bwd
         vf, vb = tower(self.vis.D, self.vis.L, self.Tv, B, False, self.wgrad_last)
         tf, tb = tower(self.txt.D, self.txt.L, self.Te, self.C, True, self.wgrad_last)

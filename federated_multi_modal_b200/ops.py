@@ -116,6 +116,12 @@ def scatter_rows(dx, rowidx, g, g_bf16):
     call("mfk_scatter_rows", dx, rowidx, g, g_bf16, dx.shape[0], dx.shape[1], stream_ptr())
 
 
+def gather_rows(src, rowidx, dst, scatter=False):
+    """dst[r] = src[rowidx[r]] (or the inverse scatter into a pre-zeroed dst); rows of equal byte length."""
+    call("mfk_gather_rows", src, rowidx, dst, rowidx.numel(), src.shape[-1] * src.element_size(), int(scatter),
+         stream_ptr())
+
+
 def transpose_bf16(inp, out, copy=None):
     """out[N, ldo] = inp[M, N]^T as bf16 (inp fp32 or bf16)."""
     call("mfk_transpose_bf16", inp, int(inp.dtype == F32), inp.stride(0), out, out.stride(0), copy,

@@ -103,6 +103,11 @@ int mfk_prompt_splice_fwd(float* x, const float* prompt, int N, int T, int row0,
 int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int N, int T, int row0, int n_ctx, int D,
                           int round_fp16, int zero_rows, void* stream);
 int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16, int R, int D, void* stream);
+/* scatter == 0: dst[r,:] = src[rowidx[r],:]; scatter != 0: dst[rowidx[r],:] = src[r,:] (dst pre-zeroed). Rows are
+ * row_bytes long (multiple of 16). Only the CLS row (clip/model.py:567) / EOT row (trainers/maple.py:76) of the
+ * last block's output is consumed, so that block's out-proj + MLP run on the gathered rows only.       */
+int mfk_gather_rows(const void* src, const int* rowidx, void* dst, int R, long long row_bytes, int scatter,
+                    void* stream);
 /* out[N, ldo] = in[M, ldi]^T as bf16 (in fp32 or bf16); optional straight bf16 copy. Used to keep
  * K-major copies of weights (dgrad) and of activations/gradients (wgrad of resblocks.11).             */
 int mfk_transpose_bf16(const void* in, int in_is_f32, long long ldi, void* out, long long ldo, void* copy,
