@@ -446,37 +446,42 @@ struct AttnTcParams {
   float c1;  // softmax scale * log2(e)
 };
 
+// Work unit = one (sequence, head): K and V are loaded once and shared by its (<= 2) 128-query tiles, whose S/O
+// accumulators use the two 256-column TMEM buffers. Q+K of the next unit are fetched as soon as this unit's QK^T
+// MMAs have retired and V is double-buffered, so TMA latency is hidden behind a whole unit of softmax work.
 template <bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw_tc[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
-  const int Tk = p.Tk, D = p.heads * HD;
-  const uint32_t kvBytes = (uint32_t)Tk * 128u;
+  const int Tk = p.Tk, D = p.heads * HD, NT = p.m_tiles;
+  const uint32_t kvBytes = (uint32_t)Tk * 128u, qBytes = (uint32_t)NT * 16384u;
   const int nkb = (Tk + 63) / 64;  // 64-key column blocks of P
-  uint8_t* sQ = smem;                       // [2][128 x 128 B]
-  uint8_t* sK = sQ + 2 * 16384;             // [2][Tk x 128 B]
-  uint8_t* sV = sK + 2 * kvBytes;           // [2][Tk x 128 B]
+  uint8_t* sQ = smem;                       // [NT x 128 rows x 128 B]
+  uint8_t* sK = sQ + qBytes;                // [Tk x 128 B]
+  uint8_t* sV = sK + kvBytes;               // [2][Tk x 128 B]
   uint8_t* sP = sV + 2 * kvBytes;           // [nkb][128 x 128 B]
   float* sx = reinterpret_cast<float*>(sP + (size_t)nkb * 16384);  // [2 halves][128 rows] max / sum exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 256);
-  uint64_t* qkv_full = bars;        // [2]
-  uint64_t* s_full = bars + 2;      // [2]
-  uint64_t* o_full = bars + 4;      // [2]
-  uint64_t* tmem_free = bars + 6;   // [2]
-  uint64_t* p_full = bars + 8;      // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* qk_full = bars;         // [1]
+  uint64_t* v_full = bars + 1;      // [2]
+  uint64_t* s_full = bars + 3;      // [2] per query tile
+  uint64_t* o_full = bars + 5;      // [2]
+  uint64_t* tmem_free = bars + 7;   // [2]
+  uint64_t* p_full = bars + 9;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_units = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == TC_SOFTMAX_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
+      mbar_init(qk_full, 1);
       for (int b = 0; b < 2; ++b) {
-        mbar_init(&qkv_full[b], 1);
+        mbar_init(&v_full[b], 1);
         mbar_init(&s_full[b], 1);
         mbar_init(&o_full[b], 1);
         mbar_init(&tmem_free[b], TC_SOFTMAX_WARPS);
@@ -495,59 +500,57 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_trigger();
   pdl_wait();
 
-  auto item_coords = [&](int i, int& n, int& h, int& mt) {
-    const int w = (int)blockIdx.x + i * (int)gridDim.x;
-    mt = w % p.m_tiles;
-    h = (w / p.m_tiles) % p.heads;
-    n = w / (p.m_tiles * p.heads);
+  auto unit_coords = [&](int u, int& n, int& h) {
+    const int w = (int)blockIdx.x + u * (int)gridDim.x;
+    h = w % p.heads;
+    n = w / p.heads;
   };
 
   if (warp == TC_SOFTMAX_WARPS) {
     // ============================ control: TMA loads + MMA issue (one thread) ============================
     if (lane == 0) {
-      auto issue_loads = [&](int i) {
-        int n, h, mt;
-        item_coords(i, n, h, mt);
-        const int b = i & 1;
-        mbar_arrive_expect_tx(&qkv_full[b], 16384u + 2u * kvBytes);
-        tma_load_2d(&tmQ, &qkv_full[b], sQ + b * 16384, h * HD, n * p.T + mt * 128);
-        tma_load_2d(&tmKV, &qkv_full[b], sK + b * kvBytes, D + h * HD, n * p.T);
-        tma_load_2d(&tmKV, &qkv_full[b], sV + b * kvBytes, 2 * D + h * HD, n * p.T);
+      auto issue_loads = [&](int u) {
+        int n, h;
+        unit_coords(u, n, h);
+        mbar_arrive_expect_tx(qk_full, qBytes + kvBytes);
+        tma_load_2d(&tmQ, qk_full, sQ, h * HD, n * p.T);
+        tma_load_2d(&tmKV, qk_full, sK, D + h * HD, n * p.T);
+        mbar_arrive_expect_tx(&v_full[u & 1], kvBytes);
+        tma_load_2d(&tmKV, &v_full[u & 1], sV + (u & 1) * kvBytes, 2 * D + h * HD, n * p.T);
       };
-      auto issue_s = [&](int i) {
-        const int b = i & 1;
-        const uint32_t par = (uint32_t)(i >> 1) & 1u;
-        mbar_wait(&qkv_full[b], par);
-        mbar_wait(&tmem_free[b], par ^ 1u);
-        tc_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(128, Tk, 0, 0);
-        const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ + b * 16384));
-        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK + b * kvBytes));
+      const uint32_t idesc_s = umma_idesc_bf16(128, Tk, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      const int ksteps = Tk / 16;
+      if (n_units > 0) issue_loads(0);
+      uint32_t pctr = 0;
+      for (int u = 0; u < n_units; ++u) {
+        const uint32_t par = (uint32_t)u & 1u;
+        mbar_wait(qk_full, par);
+        for (int mt = 0; mt < NT; ++mt) {
+          mbar_wait(&tmem_free[mt], par ^ 1u);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ) + (uint32_t)mt * 16384u);
+          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc + 2ull * k, bdesc + 2ull * k, idesc, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[b]);
-      };
-      if (n_items > 0) issue_loads(0);
-      if (n_items > 1) issue_loads(1);
-      if (n_items > 0) issue_s(0);
-      for (int i = 0; i < n_items; ++i) {
-        const int b = i & 1;
-        if (i + 1 < n_items) issue_s(i + 1);
-        mbar_wait(p_full, (uint32_t)i & 1u);
-        tc_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
-        const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV + b * kvBytes);
-        const int ksteps = Tk / 16;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t adesc = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
-          const uint64_t bdesc = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
-          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)mt * 256u, adesc + 2ull * k, bdesc + 2ull * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[mt]);
         }
-        umma_commit(&o_full[b]);
-        if (i + 2 < n_items) {
-          mbar_wait(&o_full[b], (uint32_t)(i >> 1) & 1u);  // Q/K/V buffer b (and P) no longer read
-          issue_loads(i + 2);
+        // all MMAs issued so far (incl. the previous unit's P V) have retired once s_full[NT-1] completes:
+        // Q, K and the other V buffer can be refilled for the next unit
+        mbar_wait(&s_full[NT - 1], par);
+        if (u + 1 < n_units) issue_loads(u + 1);
+        mbar_wait(&v_full[u & 1], (uint32_t)(u >> 1) & 1u);
+        const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV + (u & 1) * kvBytes);
+        for (int mt = 0; mt < NT; ++mt, ++pctr) {
+          mbar_wait(p_full, pctr & 1u);
+          tc_fence_after();
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adesc = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+            const uint64_t bdesc = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
+            umma_bf16(tmem_base + (uint32_t)mt * 256u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[mt]);
         }
       }
     }
@@ -558,11 +561,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int rl = q * 32 + lane;  // row inside the 128-row tile == TMEM lane
     const uint32_t prow = smem_u32(sP) + (uint32_t)rl * 128u;
     const uint32_t x7 = (uint32_t)rl & 7u;
-    for (int i = 0; i < n_items; ++i) {
-      int n, h, mt;
-      item_coords(i, n, h, mt);
-      const int b = i & 1;
-      const uint32_t par = (uint32_t)(i >> 1) & 1u;
+    for (int u = 0; u < n_units; ++u) {
+      int n, h;
+      unit_coords(u, n, h);
+      const uint32_t par = (uint32_t)u & 1u;
+      for (int mt = 0; mt < NT; ++mt) {
+      const int b = mt;
       const int row = mt * 128 + rl;  // query index inside the sequence
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * 256u;
       const int kmax = CAUSAL ? min(p.T, row + 1) : p.T;  // keys [0, kmax) are visible
@@ -573,13 +577,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tc_wait_ld();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: ILP instead of a 32-deep dependency
         if (!CAUSAL && c + 32 <= p.T) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < kmax) ? __uint_as_float(r[j]) : -INFINITY);
+          for (int j = 0; j < 32; ++j)
+            m4[j & 3] = fmaxf(m4[j & 3], (c + j < kmax) ? __uint_as_float(r[j]) : -INFINITY);
         }
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
       sx[half * 128 + rl] = mx;
       pair_sync(q);
@@ -599,8 +606,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int j = 0; j < 32; ++j)
             pv[j] = (c + j < kmax) ? fast_exp2(__uint_as_float(r[j]) * p.c1 - mc) : 0.f;
         }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) l += pv[j];
+        for (int j = 0; j < 32; ++j) l4[j & 3] += pv[j];
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const uint32_t blk = prow + (uint32_t)(c >> 6) * 16384u;
         const uint32_t ch0 = (uint32_t)(c & 63) >> 3;  // first 16-byte chunk of this 32-column group: 0 or 4
 #pragma unroll
@@ -645,6 +654,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_free[b]);
       pair_sync(q);  // the partner has consumed this warp's partial sum before the next item overwrites it
+      }
     }
   }
   tc_fence_before();
@@ -676,16 +686,17 @@ extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, in
   p.Tk = (T + 15) / 16 * 16;
   p.heads = heads;
   p.m_tiles = (T + 127) / 128;
-  p.total_items = N * heads * p.m_tiles;
+  p.total_items = N * heads;  // work units = (sequence, head)
   p.c1 = 0.125f * kLog2e;
   CUtensorMap tmQ, tmKV;
-  int rc = mfk_make_tmap_2d(&tmQ, qkv, 2, (uint64_t)N * T, (uint64_t)3 * D, (uint64_t)3 * D, 128, 64, 128);
+  int rc = mfk_make_tmap_2d(&tmQ, qkv, 2, (uint64_t)N * T, (uint64_t)3 * D, (uint64_t)3 * D,
+                            (uint32_t)(128 * p.m_tiles), 64, 128);
   if (rc != MFK_OK) return rc;
   if ((rc = mfk_make_tmap_2d(&tmKV, qkv, 2, (uint64_t)N * T, (uint64_t)3 * D, (uint64_t)3 * D, (uint32_t)p.Tk, 64,
                              128)) != MFK_OK)
     return rc;
   const int nkb = (p.Tk + 63) / 64;
-  const size_t smem = 2 * 16384 + 4 * (size_t)p.Tk * 128 + (size_t)nkb * 16384 + 1024 + 128 + 1024;
+  const size_t smem = (size_t)p.m_tiles * 16384 + 3 * (size_t)p.Tk * 128 + (size_t)nkb * 16384 + 1024 + 128 + 1024;
   const int grid = p.total_items < g_attn_sms ? p.total_items : g_attn_sms;
   cudaError_t e;
   if (causal) {
