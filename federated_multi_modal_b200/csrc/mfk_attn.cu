@@ -1039,7 +1039,8 @@ using namespace mfk;
 
 struct AttnBwdFusedParams {
   const float* lse;
-  const float* delta;
+  const bf16* out;    // forward output O  [rows, D]
+  const bf16* d_out;  // dO                 [rows, D]   (delta = rowsum(dO * O) is computed in-kernel)
   bf16* dqkv;
   int T, R, tiles, heads, total_units;
   float c1, scale;
@@ -1168,11 +1169,30 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       const int w = (int)blockIdx.x + u * (int)gridDim.x;
       const int h = w % p.heads, n = w / p.heads;
       const size_t sidx = ((size_t)n * p.heads + h) * p.T;
+      float dcache[2] = {0.f, 0.f};
       for (int k = 0; k < nblk; ++k, ++blk_ctr) {
         const int j = k / NT, i = k % NT;
         const int qrow = i * 128 + rl;
         const bool qok = qrow < p.T;
-        const float L = qok ? p.lse[sidx + qrow] : 0.f, Dl = qok ? p.delta[sidx + qrow] : 0.f;
+        const float L = qok ? p.lse[sidx + qrow] : 0.f;
+        if (j == 0) {  // delta[q] = sum_d dO[q,d] * O[q,d] for this head: once per query tile, kept in a register
+          float dsum = 0.f;
+          if (qok) {
+            const size_t off = ((size_t)n * p.T + qrow) * D + h * HD;
+            const uint4* po = reinterpret_cast<const uint4*>(p.out + off);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.d_out + off);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const uint4 a = __ldg(po + t), b = __ldg(pd + t);
+              const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+              const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+              dsum += (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
+                      (a3.x * b3.x + a3.y * b3.y);
+            }
+          }
+          if (i == 0) dcache[0] = dsum; else dcache[1] = dsum;
+        }
+        const float Dl = i == 0 ? dcache[0] : dcache[1];
         mbar_wait(sd_full, blk_ctr & 1u);  // also implies the previous block's second-stage MMAs retired
         tc_fence_after();
 #pragma unroll
@@ -1289,11 +1309,11 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   const int D = heads * HD;
   const long long rows = (long long)N * T;
   const long long warps = rows * heads;
-  cudaError_t e = launch_pdl(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st,
-                             static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta_ws, T, heads, rows);
-  if (e != cudaSuccess) return (int)e;
+  cudaError_t e;
+  (void)delta_ws;  // kept in the signature for symmetry with mfk_attn_bwd; delta is computed inside the kernel
   AttnBwdFusedParams p;
-  p.lse = lse; p.delta = delta_ws; p.dqkv = static_cast<bf16*>(dqkv);
+  p.lse = lse; p.out = static_cast<const bf16*>(out); p.d_out = static_cast<const bf16*>(d_out);
+  p.dqkv = static_cast<bf16*>(dqkv);
   p.T = T; p.tiles = (T + 127) / 128; p.R = p.tiles * 128; p.heads = heads;
   p.total_units = N * heads;
   p.c1 = 0.125f * kLog2e; p.scale = 0.125f;

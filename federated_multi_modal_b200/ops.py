@@ -56,7 +56,7 @@ def attn_fwd(qkv, out, lse, N, T, heads, causal, impl: Optional[str] = None):
 
 def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal, impl: Optional[str] = None):
     if impl == "fused" or (impl is None and not causal and T >= TC_ATTN_MIN_T):
-        call("mfk_attn_bwd_fused", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, stream_ptr(), kernels=2)
+        call("mfk_attn_bwd_fused", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, stream_ptr(), kernels=1)
         return
     use_tc = (TC_ATTN_MIN_T <= T <= 240) if impl is None else impl == "tc"
     call("mfk_attn_bwd_tc" if use_tc else "mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads,
