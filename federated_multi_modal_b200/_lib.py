@@ -20,6 +20,7 @@ P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 SIGNATURES = {
     "mfk_version": [],
     "mfk_error_string": [I],
+    "mfk_debug_set_attn_trace": [P],
     "mfk_gemm_bf16": [P, L, P, L, I, I, I, P, I, P, L, P, L, P, L, P, L, P, L, I, P],
     "mfk_gemm_bf16_at_b": [P, L, P, L, I, I, I, P, L, P],
     "mfk_attn_fwd": [P, P, P, I, I, I, I, P],
@@ -51,7 +52,8 @@ SIGNATURES = {
     "mfk_sgd_step": [P, P, P, L, P, P, P],
 }
 _RET = {"mfk_error_string": ctypes.c_char_p, "mfk_head_workspace_floats": L}
-_NO_STATUS = {"mfk_version", "mfk_error_string", "mfk_head_workspace_floats", "mfk_ln_bwd_ctas"}
+_NO_STATUS = {"mfk_version", "mfk_error_string", "mfk_head_workspace_floats", "mfk_ln_bwd_ctas",
+              "mfk_debug_set_attn_trace"}
 
 _lock = threading.Lock()
 _lib = None

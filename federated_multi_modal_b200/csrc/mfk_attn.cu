@@ -1044,7 +1044,13 @@ struct AttnBwdFusedParams {
   bf16* dqkv;
   int T, R, tiles, heads, total_units;
   float c1, scale;
+  long long* trace;  // optional debug: clock64 stamps of CTA 0 (see tools/attn_trace.py); NULL in production
 };
+
+#define TRC(slot)                                                             \
+  do {                                                                        \
+    if (p.trace && blockIdx.x == 0 && trc_n < 60) p.trace[(slot) * 64 + trc_n++] = clock64(); \
+  } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmDo,
@@ -1104,19 +1110,27 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       const uint32_t idesc_kt = umma_idesc_bf16(128, HD, 0, 1);  // A K-major, B MN-major (dQ)
       const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), uDo = smem_u32(sdO);
       const uint32_t uP = smem_u32(sP), uDs = smem_u32(sdS);
+      // Descriptors are built once; per MMA only a 64-bit add remains (the issuing thread is on the critical path).
+      // Strides in 16-byte units: a 128-row tile = 1024, a K-major k-step = 2, an MN-major k-step (16 rows) = 128.
+      const uint64_t dQk = umma_desc_k_sw128(uQ), dKk = umma_desc_k_sw128(uK), dVk = umma_desc_k_sw128(uV),
+                     dDok = umma_desc_k_sw128(uDo), dDsk = umma_desc_k_sw128(uDs);
+      const uint64_t dPm = umma_desc_mn_sw128(uP, 16384), dDsm = umma_desc_mn_sw128(uDs, 16384);
+      const uint64_t dDom = umma_desc_mn_sw128(uDo, 1024), dQm = umma_desc_mn_sw128(uQ, 1024),
+                     dKm = umma_desc_mn_sw128(uK, 1024);
       auto issue_sdp = [&](int i, int j) {
-        const uint64_t aq = umma_desc_k_sw128(uQ + (uint32_t)i * 16384u), bk = umma_desc_k_sw128(uK + (uint32_t)j * 16384u);
-        const uint64_t ad = umma_desc_k_sw128(uDo + (uint32_t)i * 16384u), bv = umma_desc_k_sw128(uV + (uint32_t)j * 16384u);
+        const uint64_t aq = dQk + 1024ull * i, bk = dKk + 1024ull * j, ad = dDok + 1024ull * i, bv = dVk + 1024ull * j;
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colS, aq + 2ull * k, bk + 2ull * k, idesc1, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colDP, ad + 2ull * k, bv + 2ull * k, idesc1, k > 0);
         umma_commit(sd_full);
       };
+      int trc_n = 0;
       for (int u = 0; u < n_units; ++u) {
         const int w = (int)blockIdx.x + u * (int)gridDim.x;
         const int h = w % p.heads, n = w / p.heads;
         mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
+        TRC(0);  // unit start (previous unit drained)
         mbar_arrive_expect_tx(ld_full, 4u * fullBytes);
         const int row0 = n * p.T;
         tma_load_2d(&tmQkv, ld_full, sQ, h * HD, row0);
@@ -1124,33 +1138,36 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         tma_load_2d(&tmQkv, ld_full, sV, 2 * D + h * HD, row0);
         tma_load_2d(&tmDo, ld_full, sdO, h * HD, row0);
         mbar_wait(ld_full, (uint32_t)u & 1u);
+        TRC(0);  // loads landed
         tc_fence_after();
         issue_sdp(0, 0);
+        TRC(0);  // S/dP issued
         for (int k = 0; k < nblk; ++k, ++blk_ctr) {
           const int j = k / NT, i = k % NT;
           mbar_wait(ds_full, blk_ctr & 1u);
+          TRC(0);  // staged operands ready
           if (i == 0 && j > 0) {  // accumulators of the previous key tile must have been drained
             mbar_wait(dkv_free, kt_ctr & 1u);
             ++kt_ctr;
           }
           tc_fence_after();
-          for (int ks = 0; ks < 8; ++ks) {  // dV_j += P^T dO_i   (K = 128 query rows, 16 per MMA)
-            const uint64_t a = umma_desc_mn_sw128(uP + (uint32_t)ks * 2048u, 16384);
-            const uint64_t b = umma_desc_mn_sw128(uDo + (uint32_t)i * 16384u + (uint32_t)ks * 2048u, 1024);
-            umma_bf16(tmem_base + colDV, a, b, idesc_tt, (i > 0 || ks > 0));
-          }
-          for (int ks = 0; ks < 8; ++ks) {  // dK_j += dS^T Q_i
-            const uint64_t a = umma_desc_mn_sw128(uDs + (uint32_t)ks * 2048u, 16384);
-            const uint64_t b = umma_desc_mn_sw128(uQ + (uint32_t)i * 16384u + (uint32_t)ks * 2048u, 1024);
-            umma_bf16(tmem_base + colDK, a, b, idesc_tt, (i > 0 || ks > 0));
-          }
-          for (int ks = 0; ks < 8; ++ks) {  // dQ_i += dS K_j        (K = 128 keys)
-            const uint64_t a = umma_desc_k_sw128(uDs + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
-            const uint64_t b = umma_desc_mn_sw128(uK + (uint32_t)j * 16384u + (uint32_t)ks * 2048u, 1024);
-            umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, a, b, idesc_kt, (j > 0 || ks > 0));
+          {
+            const uint64_t bdo = dDom + 1024ull * i, bq = dQm + 1024ull * i, bk = dKm + 1024ull * j;
+            const uint32_t acc_i = i > 0, acc_j = j > 0;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (K = 128 query rows, 16 per MMA)
+              umma_bf16(tmem_base + colDV, dPm + 128ull * ks, bdo + 128ull * ks, idesc_tt, acc_i | (ks > 0));
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
+              umma_bf16(tmem_base + colDK, dDsm + 128ull * ks, bq + 128ull * ks, idesc_tt, acc_i | (ks > 0));
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j        (K = 128 keys: 2 column blocks x 4 k-steps)
+              umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, dDsk + 1024ull * (ks >> 2) + 2ull * (ks & 3),
+                        bk + 128ull * ks, idesc_kt, acc_j | (ks > 0));
           }
           umma_commit(mma2_done);
           if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
+          TRC(0);  // second-stage (+ next S/dP) issued
         }
         // the last key tile's dkv_free arrive is consumed here so the phase counters stay in step
         mbar_wait(dkv_free, kt_ctr & 1u);
@@ -1165,35 +1182,44 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     const uint32_t prow = smem_u32(sP) + (uint32_t)rl * 128u, dsrow = smem_u32(sdS) + (uint32_t)rl * 128u;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t blk_ctr = 0;
+    int trc_n = 0;
+    const bool trc_me = warp == 0 && lane == 0;
     for (int u = 0; u < n_units; ++u) {
       const int w = (int)blockIdx.x + u * (int)gridDim.x;
       const int h = w % p.heads, n = w / p.heads;
       const size_t sidx = ((size_t)n * p.heads + h) * p.T;
-      float dcache[2] = {0.f, 0.f};
+      // lse and delta = rowsum(dO * O) of this thread's query row in both query tiles: fetched up front, while the
+      // control thread is still waiting for the unit's TMA loads
+      float Lc[2] = {0.f, 0.f}, dcache[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int qrow = i * 128 + rl;
+        if (i < NT && qrow < p.T) {
+          Lc[i] = p.lse[sidx + qrow];
+          const size_t off = ((size_t)n * p.T + qrow) * D + h * HD;
+          const uint4* po = reinterpret_cast<const uint4*>(p.out + off);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.d_out + off);
+          float dsum = 0.f;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint4 a = __ldg(po + t), b = __ldg(pd + t);
+            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+            const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+            dsum += (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
+                    (a3.x * b3.x + a3.y * b3.y);
+          }
+          dcache[i] = dsum;
+        }
+      }
       for (int k = 0; k < nblk; ++k, ++blk_ctr) {
         const int j = k / NT, i = k % NT;
         const int qrow = i * 128 + rl;
         const bool qok = qrow < p.T;
-        const float L = qok ? p.lse[sidx + qrow] : 0.f;
-        if (j == 0) {  // delta[q] = sum_d dO[q,d] * O[q,d] for this head: once per query tile, kept in a register
-          float dsum = 0.f;
-          if (qok) {
-            const size_t off = ((size_t)n * p.T + qrow) * D + h * HD;
-            const uint4* po = reinterpret_cast<const uint4*>(p.out + off);
-            const uint4* pd = reinterpret_cast<const uint4*>(p.d_out + off);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const uint4 a = __ldg(po + t), b = __ldg(pd + t);
-              const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-              const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
-              dsum += (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
-                      (a3.x * b3.x + a3.y * b3.y);
-            }
-          }
-          if (i == 0) dcache[0] = dsum; else dcache[1] = dsum;
-        }
+        const float L = i == 0 ? Lc[0] : Lc[1];
         const float Dl = i == 0 ? dcache[0] : dcache[1];
+        if (trc_me) TRC(1);  // about to wait for S/dP
         mbar_wait(sd_full, blk_ctr & 1u);  // also implies the previous block's second-stage MMAs retired
+        if (trc_me) TRC(1);  // S/dP ready
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -1231,9 +1257,11 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
+        if (trc_me) TRC(1);  // staged
         if (i == NT - 1) {
           // ---- key tile j complete: dK_j (scaled), dV_j -> global
           mbar_wait(mma2_done, blk_ctr & 1u);
+          if (trc_me) TRC(1);  // second-stage done
           tc_fence_after();
           const int key = j * 128 + rl;
           const size_t grow = ((size_t)n * p.T + key) * (3 * (size_t)D) + h * HD + half * 32;
@@ -1279,6 +1307,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
           }
           tc_fence_before();
           __syncwarp();
+          if (trc_me) TRC(1);  // epilogue stores issued
           if (lane == 0) {
             mbar_arrive(dkv_free);
             if (j == NT - 1) mbar_arrive(unit_free);
@@ -1295,6 +1324,13 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   }
 }
 }  // namespace
+
+static long long* g_attn_trace = nullptr;
+// debug hook: device buffer of 2*64 int64 receiving clock64 stamps of CTA 0 (NULL disables)
+extern "C" int mfk_debug_set_attn_trace(void* dev_buf) {
+  g_attn_trace = static_cast<long long*>(dev_buf);
+  return MFK_OK;
+}
 
 extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* d_out, const float* lse,
                                   float* delta_ws, void* dqkv, int N, int T, int heads, void* stream) {
@@ -1317,6 +1353,7 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   p.T = T; p.tiles = (T + 127) / 128; p.R = p.tiles * 128; p.heads = heads;
   p.total_units = N * heads;
   p.c1 = 0.125f * kLog2e; p.scale = 0.125f;
+  p.trace = g_attn_trace;
   CUtensorMap tmQkv, tmDo;
   int rc;
   if ((rc = mfk_make_tmap_2d(&tmQkv, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;

@@ -24,6 +24,9 @@ extern "C" {
 #endif
 
 int mfk_version(void);
+/* profiling aid: device buffer (2 x 64 int64) that receives clock64() stamps of CTA 0 of the fused attention
+ * backward (control thread in row 0, first compute warp in row 1); NULL (default) disables it.        */
+int mfk_debug_set_attn_trace(void* dev_buf);
 const char* mfk_error_string(int code);
 
 /* ------------------------------------------------------------------ tensor-core GEMM (tcgen05/TMEM/TMA)
