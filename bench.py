@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -328,6 +328,20 @@ def run_ours(args):
     fedavg(0)
     t_fed = timed(fedavg, 5) / 5
 
+    # ---- one federated round of this rank's client: 16 local steps + round-end FedAvg exchange + broadcast
+    # (load averaged arena, refresh bf16 copies, drop optimiser state) — BASELINE's "FedAvg round time"
+    ROUND_STEPS = 16
+    def fed_round(i):
+        for s_ in range(ROUND_STEPS):
+            trainer.step_async(*dev_pool[s_ % len(dev_pool)])
+        ex.publish(0, eng.params)
+        mean32, mean16, _, _ = ex.reduce(ex.gather())
+        eng.params[: eng.n_update].copy_(mean16)
+        eng.repack_trainable()
+        eng.reset_optimizer_state()
+    fed_round(0)
+    t_round = timed(fed_round, 2) / 2
+
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
         prof = gemm_roofline(trainer, dev_pool[0])
@@ -370,6 +384,9 @@ def run_ours(args):
                          "step_frac": step_flops / (t_dev / K) / 1e12 / peak_tf},
             "cpu_baseline": cpu,
             "fedavg_exchange_ms": t_fed * 1e3,
+            "fedavg_round_s": t_round,
+            "fedavg_round_config": f"{world} clients (1 per GPU), {ROUND_STEPS} local steps of batch {B}, all-rank "
+                                   f"exchange of the {eng.n_update}-element fp32 trainable arena + broadcast",
             "kernel_time_breakdown_ms": {k.replace("mfk_", ""): round(v["s_per_step"] * 1e3, 4) for k, v in
                                          sorted(prof.items(), key=lambda kv: -kv[1]["s_per_step"])},
             "loss": loss_now,
@@ -383,8 +400,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()

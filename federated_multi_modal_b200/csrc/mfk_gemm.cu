@@ -39,6 +39,7 @@ struct GemmParams {
   int full_tiles;   // tiles [0, full_tiles) are full width
   int split;        // each remaining big tile is split into `split` tiles of width bn/split
   int total_tiles;
+  int cluster;      // 2: CTA-pair kernel (cta_group::2); tile indices then count PAIRS of M tiles. 0: single CTAs
   const float* bias;
   int act;          // 0 none, 1 QuickGELU, 2 multiply by QuickGELU'(aux)
   const bf16* aux;
@@ -53,7 +54,7 @@ struct GemmParams {
   long long ldpre;
 };
 
-__device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0, int& n0, int& w) {
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int rank, int& m0, int& n0, int& w) {
   int big, sub = 0;
   if (t < p.full_tiles) {
     big = t;
@@ -64,7 +65,7 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0,
     sub = r % p.split;
     w = p.bn / p.split;
   }
-  m0 = (big / p.n_big) * BM;
+  m0 = ((big / p.n_big) * (p.cluster ? 2 : 1) + rank) * BM;
   n0 = (big % p.n_big) * p.bn + sub * w;
 }
 
@@ -72,7 +73,10 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& m0,
 // MN-major UMMA operands) — the wgrad form dW = dY^T X straight from the row-major activations, no transposes.
 // EPI selects the epilogue at compile time (keeps each variant's register footprint small):
 //   0 plain (+bias)   1 bias + QuickGELU (+pre-activation store)   2 * QuickGELU'(aux)   3 (+bias) + fp32 residual
-template <int BN, int kStages, bool kMN, int EPI>
+// kPair: launched as clusters of 2 CTAs; tcgen05 cta_group::2 — one UMMA of M = 256 spans the pair, each CTA keeps its
+// own 128 A rows and HALF of the B rows in smem (the tensor cores of the two SMs exchange the halves), which halves
+// the shared-memory traffic per SM; the leader CTA issues all MMAs, both CTAs run producers and epilogues.
+template <int BN, int kStages, bool kMN, int EPI, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -93,6 +97,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
+  // pair mode: the two CTAs of a cluster work on vertically adjacent M tiles of the same N range
+  const int crank = kPair ? (int)cluster_ctarank() : 0;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -108,16 +116,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_2sm(tmem_slot, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above overlapped the tail of the previous kernel (PDL); from here on global memory is touched
@@ -129,14 +143,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tstep) {
         int m0, n0, w;
-        decode_tile(p, t, m0, n0, w);
+        decode_tile(p, t, crank, m0, n0, w);
         const uint32_t tx = kABytes + (uint32_t)w * BK * 2;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
+          if (!kMN && kPair) {
+            // pair mode: this CTA fetches its own A rows and its half of the B rows; all bytes of both CTAs are
+            // accounted on the LEADER's full barrier (the leader alone issues the MMAs)
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * kABytes + (uint32_t)w * BK * 2);
+            const uint32_t lead_bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2sm(&tmA, lead_bar, sa, kb * BK, m0);
+            const int hw = w >> 1;
+            for (int j = 0; j < hw; j += 32)
+              tma_load_2d_2sm(&tmB, lead_bar, sb + j * (BK * 2), kb * BK, n0 + crank * hw + j);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           if (!kMN) {
             tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
@@ -156,18 +182,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    if (lane == 0 && !(kPair && crank != 0)) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < p.total_tiles; t += tstep, ++it) {
         int m0, n0, w;
-        decode_tile(p, t, m0, n0, w);
+        decode_tile(p, t, crank, m0, n0, w);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(BM, w, kMN ? 1 : 0, kMN ? 1 : 0);
+        const uint32_t idesc = umma_idesc_bf16(kPair ? 2 * BM : BM, w, kMN ? 1 : 0, kMN ? 1 : 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -178,14 +204,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // per UMMA_K = 16: K-major advances 32 B inside the swizzle row (+2 in 16-byte units); MN-major
           // advances 16 K-rows of 128 B (+128 in 16-byte units)
           constexpr uint64_t kStep = kMN ? 128 : 2;
+          if (kPair) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            umma_bf16(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k)
+              umma_bf16_2sm(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              umma_bf16(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete
+        if (kPair) umma_commit_2sm_mc(&tfull_bar[acc], (uint16_t)3);  // both CTAs' epilogues wake
+        else umma_commit(&tfull_bar[acc]);                                    // accumulator complete
       }
     }
     __syncwarp();
@@ -206,7 +239,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto fetch_ops = [&](int t, int c) {
       if (t >= p.total_tiles) return;
       int m0, n0, w;
-      decode_tile(p, t, m0, n0, w);
+      decode_tile(p, t, crank, m0, n0, w);
       const int row = m0 + q * 32 + lane, col = n0 + c;
       if (c >= w || row >= p.M || col >= p.N) return;
       if (EPI == 3) {
@@ -220,11 +253,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < 4; ++j) av_nx[j] = __ldg(a4 + j);
       }
     };
-    fetch_ops(blockIdx.x, half * 32);
+    fetch_ops(tile0, half * 32);
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < p.total_tiles; t += tstep, ++it) {
       int m0, n0, w;
-      decode_tile(p, t, m0, n0, w);
+      decode_tile(p, t, crank, m0, n0, w);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m0 + q * 32 + lane;
@@ -246,7 +279,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (EPI >= 2) {  // next chunk of this tile, else the first chunk of this CTA's next tile
           if (c + 64 < w) fetch_ops(t, c + 64);
-          else fetch_ops(t + (int)gridDim.x, half * 32);
+          else fetch_ops(t + tstep, half * 32);
         }
         if (!waited) {
           mbar_wait(&tfull_bar[acc], acc_phase);
@@ -342,16 +375,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kPair && crank != 0) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output stores complete before exit
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it is done too
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -421,20 +459,20 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int kStages, bool kMN, int EPI>
+template <int BN, int kStages, bool kMN, int EPI, bool kPair = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO32,
                        const CUtensorMap& tmO16, const CUtensorMap& tmPre, const GemmParams& p, int grid,
                        cudaStream_t st) {
   static bool configured = false;
   constexpr size_t smem = gemm_smem_bytes<BN, kStages>();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages, kMN, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kStages, kMN, EPI, kPair>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BN, kStages, kMN, EPI>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB,
-                              tmO32, tmO16, tmPre, p);
+  cudaError_t le = launch_pdl_cluster(gemm_bf16_tn_kernel<BN, kStages, kMN, EPI, kPair>, dim3(grid), dim3(kThreads), smem,
+                                      st, kPair ? 2 : 1, tmA, tmB, tmO32, tmO16, tmPre, p);
   if (le != cudaSuccess) return (int)le;
   return MFK_OK;
 }
@@ -455,19 +493,24 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
   const int sms = num_sms();
   const int m_tiles = (M + BM - 1) / BM;
   // full tile width: 256 unless N is small or the caller forces 128
-  int bn = (tile_n == 128 || tile_n == 256) ? tile_n : 256;
+  int bn = (tile_n == 128) ? 128 : 256;  // tile_n == 2 selects the CTA-pair (cta_group::2) kernel with 256-wide tiles
   if (tile_n == 0 && N < 256) bn = 128;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.bn = bn;
   p.n_big = (N + bn - 1) / bn;
-  const int big = m_tiles * p.n_big;
-  p.full_tiles = (big / sms) * sms;
+  // CTA-pair kernel (tcgen05 cta_group::2, UMMA M = 256) on request. It halves per-SM shared-memory traffic, which
+  // pays for long K loops (8192^3: +3 %); the MaPLe shapes (K <= 3072, <= 4 tiles per SM) are bound by per-launch
+  // fixed costs instead and are as fast with single CTAs, so `auto` keeps those.
+  p.cluster = (tile_n == 2 && m_tiles >= 2) ? 2 : 0;
+  const int units = p.cluster ? sms / 2 : sms;                      // schedulable CTAs or CTA pairs
+  const int big = (p.cluster ? (m_tiles + 1) / 2 : m_tiles) * p.n_big;
+  p.full_tiles = (big / units) * units;
   const int rem = big - p.full_tiles;
   p.split = 1;
   if (rem > 0) {
     const int max_split = bn / 64;
-    while (p.split * 2 <= max_split && rem * p.split * 2 <= sms) p.split *= 2;
+    while (p.split * 2 <= max_split && rem * p.split * 2 <= units) p.split *= 2;
   }
   p.total_tiles = p.full_tiles + rem * p.split;
   p.bias = bias; p.act = act;
@@ -480,7 +523,7 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
   CUtensorMap tmA, tmB;
   int rc = mfk_make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
   if (rc != MFK_OK) return rc;
-  rc = mfk_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BOXN, BK);
+  rc = mfk_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, p.cluster ? 32 : BOXN, BK);
   if (rc != MFK_OK) return rc;
   // output tensor maps: 32-row x 32-column boxes (one epilogue warp's chunk); absent outputs get a dummy map
   CUtensorMap tmO32 = tmA, tmO16 = tmA, tmPre = tmA;
@@ -491,7 +534,8 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
   if (out_pre_bf16 &&
       (rc = mfk_make_tmap_2d(&tmPre, out_pre_bf16, 2, (uint64_t)M, (uint64_t)N, (uint64_t)ldpre, 32, 32, 64)))
     return rc;
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int grid = p.cluster ? 2 * (p.total_tiles < units ? p.total_tiles : units)
+                             : (p.total_tiles < sms ? p.total_tiles : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int epi = act == 1 ? 1 : act == 2 ? 2 : residual ? 3 : 0;
 #define MFK_GEMM_DISPATCH(BN_, ST_)                                                                           \
@@ -500,6 +544,14 @@ extern "C" int mfk_gemm_bf16(const void* A, long long lda, const void* B, long l
     case 1: return launch_gemm<BN_, ST_, false, 1>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);               \
     case 2: return launch_gemm<BN_, ST_, false, 2>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);               \
     default: return launch_gemm<BN_, ST_, false, 3>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);              \
+  }
+  if (p.cluster == 2) {
+    switch (epi) {
+      case 0: return launch_gemm<256, 4, false, 0, true>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+      case 1: return launch_gemm<256, 4, false, 1, true>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+      case 2: return launch_gemm<256, 4, false, 2, true>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+      default: return launch_gemm<256, 4, false, 3, true>(tmA, tmB, tmO32, tmO16, tmPre, p, grid, st);
+    }
   }
   if (bn == 256) { MFK_GEMM_DISPATCH(256, 4) }
   MFK_GEMM_DISPATCH(128, 6)
@@ -526,6 +578,7 @@ extern "C" int mfk_gemm_bf16_at_b(const void* At, long long lda, const void* Bt,
     while (p.split * 2 <= 4 && rem * p.split * 2 <= sms) p.split *= 2;
   p.total_tiles = p.full_tiles + rem * p.split;
   p.out32 = out_f32; p.ld32 = ld32;
+  p.cluster = 0;
   CUtensorMap tmA, tmB, tmO32;
   int rc = mfk_make_tmap_2d(&tmA, At, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 64, 128);
   if (rc != MFK_OK) return rc;

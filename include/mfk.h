@@ -34,7 +34,8 @@ const char* mfk_error_string(int code);
  *   epi: (+bias[N] fp32) -> act -> (+residual[M,N] fp32) -> out_f32 and/or out_bf16
  *   act 0: none | 1: QuickGELU x*sigmoid(1.702x), pre-activation optionally stored (out_pre_bf16)
  *       2: multiply by QuickGELU'(aux[M,N] bf16)   (backward of act 1)
- * N % 32 == 0. tile_n: 0 = auto, 128 or 256 = forced full-tile width.
+ * N % 32 == 0. tile_n: 0 = auto, 128 or 256 = forced full-tile width, 2 = CTA-pair kernel (cta_group::2, M = 256
+ * per pair, each CTA holds half of every B tile).
  * Replaces: nn.MultiheadAttention in_proj/out_proj (clip/model.py:274,303-305,350), mlp.c_fc +
  * QuickGELU + c_proj (clip/model.py:276-280,162-164,351), conv1 as GEMM (clip/model.py:484,514),
  * `x @ self.proj` (clip/model.py:569-570), `@ self.text_projection` (trainers/maple.py:76), and

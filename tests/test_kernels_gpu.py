@@ -33,7 +33,7 @@ GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (100, 64, 72), (6368, 2304, 768)
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("tile_n", [0, 128])
+@pytest.mark.parametrize("tile_n", [0, 128, 2])  # auto | 128-wide tiles | CTA-pair (cta_group::2) kernel
 def test_gemm_plain(M, N, K, tile_n):
     a, b = rnd(M, K, dtype=BF16, seed=1), rnd(N, K, std=K ** -0.5, dtype=BF16, seed=2)
     out32 = torch.full((M, N), float("nan"), device=DEV, dtype=F32)
@@ -48,28 +48,29 @@ def test_gemm_plain(M, N, K, tile_n):
 
 
 @pytest.mark.parametrize("M,N,K", [(6368, 768, 768), (770, 512, 512), (200, 96, 128)])
-def test_gemm_epilogues(M, N, K):
+@pytest.mark.parametrize("tile_n", [0, 2])
+def test_gemm_epilogues(M, N, K, tile_n):
     a, b = rnd(M, K, dtype=BF16, seed=3), rnd(N, K, std=K ** -0.5, dtype=BF16, seed=4)
     bias = rnd(N, std=0.1, seed=5)
     res = rnd(M, N, seed=6)
     ref = a.float() @ b.float().t() + bias
     # bias + residual -> fp32
     out32 = torch.empty(M, N, device=DEV, dtype=F32)
-    ops.gemm(a, b, bias=bias, residual=res, out_f32=out32)
+    ops.gemm(a, b, bias=bias, residual=res, out_f32=out32, tile_n=tile_n)
     assert (out32 - (ref + res)).abs().max().item() < 5e-3
     # in-place residual (out aliases residual), as the towers use it
     x = res.clone()
-    ops.gemm(a, b, bias=bias, residual=x, out_f32=x)
+    ops.gemm(a, b, bias=bias, residual=x, out_f32=x, tile_n=tile_n)
     assert (x - (ref + res)).abs().max().item() < 5e-3
     # QuickGELU with pre-activation saved
     act = torch.empty(M, N, device=DEV, dtype=BF16)
     pre = torch.empty(M, N, device=DEV, dtype=BF16)
-    ops.gemm(a, b, bias=bias, act=1, out_bf16=act, out_pre=pre)
+    ops.gemm(a, b, bias=bias, act=1, out_bf16=act, out_pre=pre, tile_n=tile_n)
     assert (pre.float() - ref).abs().max().item() < 3e-2
     assert (act.float() - qgelu(pre.float())).abs().max().item() < 2e-2
     # backward of QuickGELU: multiply by gelu'(aux)
     dg = torch.empty(M, N, device=DEV, dtype=BF16)
-    ops.gemm(a, b, act=2, aux=pre, out_bf16=dg)
+    ops.gemm(a, b, act=2, aux=pre, out_bf16=dg, tile_n=tile_n)
     want = (a.float() @ b.float().t()) * dqgelu(pre.float())
     assert (dg.float() - want).abs().max().item() < 3e-2
 
