@@ -182,6 +182,8 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, int P, 
 template <bool IN_BF16>
 __global__ void colsum_partial_kernel(const void* __restrict__ x_, long long ld, int M, int N,
                                       float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   // block (32, 8): 64 columns per block.x, rows strided by 8*gridDim.y
   const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
   __shared__ float red[8][64];
@@ -288,6 +290,8 @@ __global__ void text_assemble_kernel(const float* __restrict__ prefix, const flo
 // clip/model.py:320-349: overwrite n_ctx rows of every sequence with q16(prompt).
 __global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict__ prompt, int T, int row0, int n_ctx,
                                   int D) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x / n_ctx, j = blockIdx.x % n_ctx;
   float* dst = x + ((size_t)b * T + row0 + j) * D;
   const float* src = prompt + (size_t)j * D;
@@ -301,6 +305,8 @@ __global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict
 // 0..7 (for N <= 8 this is the plain sequential batch order of autograd's expand-backward).
 __global__ void splice_bwd_kernel(float* __restrict__ g, bf16* __restrict__ g16, float* __restrict__ dprompt, int N,
                                   int T, int row0, int n_ctx, int D, int round16, int zero) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int j = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -329,6 +335,8 @@ __global__ void splice_bwd_kernel(float* __restrict__ g, bf16* __restrict__ g16,
 // g[rowidx[r], :] = dx[r, :] (+ bf16 copy); g must have been zero-filled.
 __global__ void scatter_rows_kernel(const float* __restrict__ dx, const int* __restrict__ rowidx,
                                     float* __restrict__ g, bf16* __restrict__ g16, int D) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const size_t dst = (size_t)rowidx[r] * D;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -341,6 +349,8 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dx, const int* __r
 // dst[r, :] = src[rowidx[r], :] in 16-byte chunks (row_bytes % 16 == 0)
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ rowidx,
                                    uint4* __restrict__ dst, int chunks_per_row) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const size_t s0 = (size_t)rowidx[r] * chunks_per_row, d0 = (size_t)r * chunks_per_row;
   for (int i = threadIdx.x; i < chunks_per_row; i += blockDim.x) dst[d0 + i] = src[s0 + i];
@@ -348,6 +358,8 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __r
 // dst[rowidx[r], :] = src[r, :] (bf16 rows); dst must have been zero-filled
 __global__ void scatter_rows_bf16_kernel(const uint4* __restrict__ src, const int* __restrict__ rowidx,
                                          uint4* __restrict__ dst, int chunks_per_row) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const size_t d0 = (size_t)rowidx[r] * chunks_per_row, s0 = (size_t)r * chunks_per_row;
   for (int i = threadIdx.x; i < chunks_per_row; i += blockDim.x) dst[d0 + i] = src[s0 + i];
@@ -506,10 +518,10 @@ extern "C" int mfk_colsum(const void* x, int is_bf16, long long ld, int M, int N
   if (!x || !out || !partial_ws || M <= 0 || N <= 0 || (N & 1)) return MFK_EARG;
   const int P = 32;
   dim3 grid((N + 63) / 64, P), block(32, 8);
-  if (is_bf16) colsum_partial_kernel<true><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
-  else colsum_partial_kernel<false><<<grid, block, 0, ST(stream)>>>(x, ld, M, N, partial_ws);
-  partial_reduce_kernel<<<dim3((N + 31) / 32, 1), dim3(32, 32), 0, ST(stream)>>>(partial_ws, P, N, N, 0, out, nullptr,
-                                                                                accumulate);
+  if (is_bf16) launch_pdl(colsum_partial_kernel<true>, grid, block, 0, ST(stream), x, ld, M, N, partial_ws);
+  else launch_pdl(colsum_partial_kernel<false>, grid, block, 0, ST(stream), x, ld, M, N, partial_ws);
+  launch_pdl(partial_reduce_kernel, dim3((N + 31) / 32, 1), dim3(32, 32), 0, ST(stream), (const float*)partial_ws, P, N,
+             (long long)N, 0LL, out, (float*)nullptr, accumulate);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -544,7 +556,7 @@ extern "C" int mfk_text_assemble(const float* prefix, const float* ctx, const fl
 extern "C" int mfk_prompt_splice_fwd(float* x, const float* prompt, int N, int T, int row0, int n_ctx, int D,
                                      void* stream) {
   if (!x || !prompt || row0 < 0 || row0 + n_ctx > T || D % 4) return MFK_EARG;
-  splice_fwd_kernel<<<N * n_ctx, 128, 0, ST(stream)>>>(x, prompt, T, row0, n_ctx, D);
+  launch_pdl(splice_fwd_kernel, dim3(N * n_ctx), dim3(128), 0, ST(stream), x, prompt, T, row0, n_ctx, D);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -553,8 +565,8 @@ extern "C" int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int
                                      int round_fp16, int zero_rows, void* stream) {
   if (!g || !dprompt || row0 < 0 || row0 + n_ctx > T) return MFK_EARG;
   dim3 grid((D + 31) / 32, n_ctx);
-  splice_bwd_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(g, static_cast<bf16*>(g_bf16), dprompt, N, T, row0, n_ctx, D,
-                                                  round_fp16, zero_rows);
+  launch_pdl(splice_bwd_kernel, grid, dim3(32, 8), 0, ST(stream), g, static_cast<bf16*>(g_bf16), dprompt, N, T, row0,
+             n_ctx, D, round_fp16, zero_rows);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -562,7 +574,7 @@ extern "C" int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int
 extern "C" int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16, int R, int D,
                                 void* stream) {
   if (!dx || !rowidx || !g || R <= 0) return MFK_EARG;
-  scatter_rows_kernel<<<R, 128, 0, ST(stream)>>>(dx, rowidx, g, static_cast<bf16*>(g_bf16), D);
+  launch_pdl(scatter_rows_kernel, dim3(R), dim3(128), 0, ST(stream), dx, rowidx, g, static_cast<bf16*>(g_bf16), D);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
@@ -572,9 +584,11 @@ extern "C" int mfk_gather_rows(const void* src, const int* rowidx, void* dst, in
   if (!src || !rowidx || !dst || R <= 0 || row_bytes <= 0 || row_bytes % 16) return MFK_EARG;
   const int chunks = (int)(row_bytes / 16);
   if (scatter)
-    scatter_rows_bf16_kernel<<<R, 128, 0, ST(stream)>>>(static_cast<const uint4*>(src), rowidx, static_cast<uint4*>(dst), chunks);
+    launch_pdl(scatter_rows_bf16_kernel, dim3(R), dim3(128), 0, ST(stream), static_cast<const uint4*>(src), rowidx,
+               static_cast<uint4*>(dst), chunks);
   else
-    gather_rows_kernel<<<R, 128, 0, ST(stream)>>>(static_cast<const uint4*>(src), rowidx, static_cast<uint4*>(dst), chunks);
+    launch_pdl(gather_rows_kernel, dim3(R), dim3(128), 0, ST(stream), static_cast<const uint4*>(src), rowidx,
+               static_cast<uint4*>(dst), chunks);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

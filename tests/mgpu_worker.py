@@ -85,6 +85,40 @@ def main():
         a = eng.logits(img.to(dev), cache_text=False, shard_classes=True)
         b = eng.logits(img.to(dev), cache_text=False, shard_classes=False)
         assert torch.equal(a, b), (a - b).abs().max()
+    if backend == "nccl":
+        # end-to-end: MaPLeFederated.train() with 2 clients per rank, one round; every rank must end with the same
+        # global arena, equal to the fixed-order mean of ALL clients' published arenas
+        import contextlib, io
+        from federated_multi_modal_b200.trainers import ClientDataManager, MaPLeFederated
+        from federated_multi_modal_b200.trainers.client_datamanager import synthetic_client_items
+        Cn, Kc = 4, 2 * world
+        cfg = synth.make_cfg()
+        cfg.FED.NUM_CLIENTS, cfg.FED.NUM_ROUNDS, cfg.FED.LOCAL_EPOCHS = Kc, 1, 1
+        cfg.DATALOADER = synth._NS(TRAIN_X=synth._NS(BATCH_SIZE=2), TEST=synth._NS(BATCH_SIZE=4))
+        cfg.OUTPUT_DIR = ""
+        names = synth.synthetic_classnames(Cn)
+        pool = synthetic_client_items(Cn, Kc, seed=3, classnames=names)          # Cn*Kc images
+        dms = [ClientDataManager(pool[k::Kc][:2] + pool[k::Kc][2:4], [], [], cfg) for k in range(Kc)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            fed = MaPLeFederated(cfg, client_data_managers=dms, classnames=names)
+            assert [t.client_id for t in fed.clients] == clients_of_rank(Kc, rank, world)
+            captured = {}
+            orig = fed._aggregate
+            def spy():
+                captured["rows"] = [r.clone().cpu() for r in fed.exchange.gather()]
+                return orig()
+            fed._aggregate = spy
+            fed.train()
+        assert len(captured["rows"]) == Kc
+        m32, m16 = fedavg_oracle(captured["rows"])
+        assert torch.equal(fed.last_mean_fp32.cpu(), m32)
+        assert torch.equal(fed.global_arena.cpu(), m16.float())
+        chk = fed.global_arena.double().sum().reshape(1).clone()
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        assert all(torch.equal(x, lst[0]) for x in lst)
+        # local training really differs between clients (different data) before it is averaged
+        assert not torch.equal(captured["rows"][0], captured["rows"][Kc - 1])
     if rank == 0:
         print(f"MGPU_OK backend={backend} world={world} transport={ex.transport}")
     dist.barrier()
