@@ -46,7 +46,7 @@ class _Tower:
 class MapleEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], tokenized_prompts: torch.Tensor, *, n_ctx: int = 2,
                  depth: int = 9, device: str = "cuda", trainable: str = "reference", text_truncate: bool = True,
-                 patch: int = 16, share_from: Optional["MapleEngine"] = None):
+                 patch: int = 16, share_from: Optional["MapleEngine"] = None, share_workspace: bool = True):
         """``share_from``: another engine on the same GPU (a co-located federated client). The frozen packed
         CLIP weights and the activation workspaces are shared with it; only the trainable arena, its
         gradient/momentum arenas and the bf16 copies of trainable block weights are per client."""
@@ -73,7 +73,7 @@ class MapleEngine:
         self.Tv = self.P + 1 + n_ctx
         self._build_arena(sd)
         self._pack_frozen(sd, share_from)
-        self._bufs: Dict[str, torch.Tensor] = share_from._bufs if share_from is not None else {}
+        self._bufs: Dict[str, torch.Tensor] = share_from._bufs if (share_from is not None and share_workspace) else {}
         self._Bmax = 0
         self._text_cache_valid = False
         self.mom_initialized = False
