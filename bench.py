@@ -234,21 +234,21 @@ def gemm_probe(eng, reps=5):
     dgrads), 12 layers back to back (operands of consecutive launches differ; the 12-layer set is ~1.5 GB >> L2)."""
     from federated_multi_modal_b200 import ops
     tw = eng.vis
-    ws, M, D = tw.ws, tw.M, tw.D
+    ws, M, D, gw = tw.ws, tw.M, tw.D, tw.gemm_ws
 
     def run():
         for l in range(tw.L):
             w = tw.w[l]
-            ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=ws["qkv"][l])
+            ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=ws["qkv"][l], ws=gw)
             ops.gemm(ws["att"][l], w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=ws["x1"][l],
-                     out_f32=ws["x2"][l])
-            ops.gemm(ws["h2"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act"], out_pre=ws["u"][l])
+                     out_f32=ws["x2"][l], ws=gw)
+            ops.gemm(ws["h2"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act"], out_pre=ws["u"][l], ws=gw)
             ops.gemm(ws["act"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=ws["x2"][l],
-                     out_f32=ws["x1"][l + 1])
-            ops.gemm(ws["g16"], w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"])
-            ops.gemm(ws["du"], w["mlp.c_fc.wT"], out_bf16=ws["dh"])
-            ops.gemm(ws["g16"], w["attn.out_proj.wT"], out_bf16=ws["dh"])
-            ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"])
+                     out_f32=ws["x1"][l + 1], ws=gw)
+            ops.gemm(ws["g16"], w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"], ws=gw)
+            ops.gemm(ws["du"], w["mlp.c_fc.wT"], out_bf16=ws["dh"], ws=gw)
+            ops.gemm(ws["g16"], w["attn.out_proj.wT"], out_bf16=ws["dh"], ws=gw)
+            ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"], ws=gw)
     run()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

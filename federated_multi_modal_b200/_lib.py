@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfk.so")
+LIB_PATH = os.environ.get("MFK_LIB_PATH") or os.path.join(_HERE, "libmfk.so")  # env: A/B experiment builds
 
 P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 
@@ -21,7 +21,8 @@ SIGNATURES = {
     "mfk_version": [],
     "mfk_error_string": [I],
     "mfk_debug_set_attn_trace": [P],
-    "mfk_gemm_bf16": [P, L, P, L, I, I, I, P, I, P, L, P, L, P, L, P, L, P, L, I, P],
+    "mfk_debug_set_gemm_trace": [P],
+    "mfk_gemm_bf16": [P, L, P, L, I, I, I, P, I, P, L, P, L, P, L, P, L, P, L, I, P, L, P],
     "mfk_gemm_bf16_at_b": [P, L, P, L, I, I, I, P, L, P],
     "mfk_attn_fwd": [P, P, P, I, I, I, I, P],
     "mfk_attn_fwd_tc": [P, P, P, I, I, I, I, P],
@@ -53,7 +54,7 @@ SIGNATURES = {
 }
 _RET = {"mfk_error_string": ctypes.c_char_p, "mfk_head_workspace_floats": L}
 _NO_STATUS = {"mfk_version", "mfk_error_string", "mfk_head_workspace_floats", "mfk_ln_bwd_ctas",
-              "mfk_debug_set_attn_trace"}
+              "mfk_debug_set_attn_trace", "mfk_debug_set_gemm_trace"}
 
 _lock = threading.Lock()
 _lib = None

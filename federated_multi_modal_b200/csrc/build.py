@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-LIB = os.path.join(PKG, "libmfk.so")
+LIB = os.environ.get("MFK_LIB_OUT") or os.path.join(PKG, "libmfk.so")
 SOURCES = ["mfk_gemm.cu", "mfk_attn.cu", "mfk_elem.cu", "mfk_head.cu", "mfk_fed.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -36,6 +36,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("MFK_DEFS", "").split()  # experiment builds (tools/ab_step.sh), e.g. -DMFK_NO_GTRACE
+    if os.environ.get("MFK_LIB_OUT"):
+        objdir = objdir + "_" + os.path.basename(LIB).replace(".", "_")
+        os.makedirs(objdir, exist_ok=True)
 
     def cc(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

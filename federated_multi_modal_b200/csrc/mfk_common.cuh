@@ -26,6 +26,11 @@ static inline bool mfk_aligned16(const void* p) { return (reinterpret_cast<uintp
 namespace mfk {
 
 // ----------------------------------------------------------------------------- misc
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

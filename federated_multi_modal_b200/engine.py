@@ -41,6 +41,7 @@ class _Tower:
         self.w: List[Dict[str, torch.Tensor]] = []  # per layer packed tensors
         self.N = self.T = self.M = 0
         self.ws: Dict[str, torch.Tensor] = {}
+        self.gemm_ws: Optional[torch.Tensor] = None  # split-K workspace (vision tower only: one user stream)
 
 
 class MapleEngine:
@@ -74,6 +75,11 @@ class MapleEngine:
         self._build_arena(sd)
         self._pack_frozen(sd, share_from)
         self._bufs: Dict[str, torch.Tensor] = share_from._bufs if (share_from is not None and share_workspace) else {}
+        # split-K tail workspace of the vision-tower GEMMs (main stream only; the text tower runs concurrently on a
+        # side stream and a workspace must never be shared by two streams)
+        if "__gemm_ws__" not in self._bufs:
+            self._bufs["__gemm_ws__"] = ops.splitk_workspace(self.dev)
+        self.vis.gemm_ws = self._bufs["__gemm_ws__"]
         self._Bmax = 0
         self._text_cache_valid = False
         self.mom_initialized = False
@@ -290,7 +296,7 @@ class MapleEngine:
         st = ws["stat"][l] if train else (None, None, None, None)
         ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_bf16=ws["h"], mean=st[0], rstd=st[1])
         qkv, att = ws["qkv"][s], ws["att"][s]
-        ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=qkv)
+        ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=qkv, ws=tw.gemm_ws)
         ops.attn_fwd(qkv, att, ws["lse"][l] if train else None, tw.N, tw.T, tw.heads, tw.causal)
         if rows is not None:
             sr = ws["stat_r"] if train else (None, None)
@@ -304,11 +310,11 @@ class MapleEngine:
             ops.gemm(ws["act_r"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=ws["x2_r"],
                      out_f32=ws["xout_r"])
             return ws["xout_r"]
-        ops.gemm(att, w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=x1, out_f32=x2)
+        ops.gemm(att, w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=x1, out_f32=x2, ws=tw.gemm_ws)
         ops.layernorm_fwd(x2, w["ln_2.g"], w["ln_2.b"], y_bf16=ws["h2"], mean=st[2], rstd=st[3])
         ops.gemm(ws["h2"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act"],
-                 out_pre=ws["u"][l] if train else None)
-        ops.gemm(ws["act"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=x2, out_f32=x1n)
+                 out_pre=ws["u"][l] if train else None, ws=tw.gemm_ws)
+        ops.gemm(ws["act"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=x2, out_f32=x1n, ws=tw.gemm_ws)
         return x1n
 
     def _tower_fwd(self, tw: _Tower, deep: List[torch.Tensor], row0: int, train: bool, rows=None):
@@ -366,7 +372,7 @@ class MapleEngine:
             da = ws["dh"]
             ops.attn_bwd(ws["qkv"][l], ws["att"][l], da, ws["lse"][l], ws["delta"], ws["dqkv"], tw.N, tw.T, tw.heads,
                          tw.causal)
-            ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"])
+            ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"], ws=tw.gemm_ws)
             if wg:
                 self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)
                 ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
@@ -375,11 +381,11 @@ class MapleEngine:
                               dbeta=G[pre + "ln_1.bias"] if ln_grads else None, partial_ws=ws["lnp"])
             return
         # ---- MLP branch
-        ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"])
+        ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"], ws=tw.gemm_ws)
         if wg:
             self._wgrad(tw, g16, ws["act"], G[pre + "mlp.c_proj.weight"], D, 4 * D)
             ops.colsum(g, G[pre + "mlp.c_proj.bias"], ws["csum"])
-        ops.gemm(ws["du"], w["mlp.c_fc.wT"], out_bf16=ws["dh"])
+        ops.gemm(ws["du"], w["mlp.c_fc.wT"], out_bf16=ws["dh"], ws=tw.gemm_ws)
         if wg:
             self._wgrad(tw, ws["du"], ws["h2"], G[pre + "mlp.c_fc.weight"], 4 * D, D)
             ops.colsum(ws["du"], G[pre + "mlp.c_fc.bias"], ws["csum"])
@@ -388,13 +394,13 @@ class MapleEngine:
                           dbeta=G[pre + "ln_2.bias"] if ln_grads else None, partial_ws=ws["lnp"])
         # ---- attention branch
         da = ws["dh"]
-        ops.gemm(g16, w["attn.out_proj.wT"], out_bf16=da)
+        ops.gemm(g16, w["attn.out_proj.wT"], out_bf16=da, ws=tw.gemm_ws)
         if wg:
             self._wgrad(tw, g16, ws["att"][l], G[pre + "attn.out_proj.weight"], D, D)
             ops.colsum(g, G[pre + "attn.out_proj.bias"], ws["csum"])
         ops.attn_bwd(ws["qkv"][l], ws["att"][l], da, ws["lse"][l], ws["delta"], ws["dqkv"], tw.N, tw.T, tw.heads,
                      tw.causal)
-        ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"])
+        ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"], ws=tw.gemm_ws)
         if wg:
             self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)
             ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])

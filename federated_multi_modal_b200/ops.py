@@ -27,14 +27,25 @@ def _chk(t: torch.Tensor, dtype, name: str):
 def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = 0,
          aux: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
-         out_pre: Optional[torch.Tensor] = None, k: Optional[int] = None, tile_n: int = 0):
-    """out[M,N] = epi(a[M,K] @ b[N,K]^T); see mfk_gemm_bf16. `k` overrides K (padded operands)."""
+         out_pre: Optional[torch.Tensor] = None, k: Optional[int] = None, tile_n: int = 0,
+         ws: Optional[torch.Tensor] = None):
+    """out[M,N] = epi(a[M,K] @ b[N,K]^T); see mfk_gemm_bf16. `k` overrides K (padded operands). `ws`: zero-filled
+    split-K workspace (splitk_workspace()) owned by the GEMMs of one stream; None disables the split-K tail."""
     _chk(a, BF16, "a"); _chk(b, BF16, "b")
     M, N = a.shape[0], b.shape[0]
     K = a.shape[1] if k is None else k
     ld = lambda t: t.stride(0) if t is not None else 0
     call("mfk_gemm_bf16", a, a.stride(0), b, b.stride(0), M, N, K, bias, act, aux, ld(aux), residual, ld(residual),
-         out_f32, ld(out_f32), out_bf16, ld(out_bf16), out_pre, ld(out_pre), tile_n, stream_ptr())
+         out_f32, ld(out_f32), out_bf16, ld(out_bf16), out_pre, ld(out_pre), tile_n, ws,
+         ws.numel() * ws.element_size() if ws is not None else 0, stream_ptr())
+
+
+SPLITK_WS_BYTES = 4096 + 148 * 128 * 256 * 4
+
+
+def splitk_workspace(device) -> torch.Tensor:
+    """Zero-filled workspace for the split-K tail of ops.gemm (one per stream that runs large GEMMs)."""
+    return torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=F32)
 
 
 def gemm_at_b(at: torch.Tensor, bt: torch.Tensor, out_f32: torch.Tensor):

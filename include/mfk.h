@@ -27,6 +27,9 @@ int mfk_version(void);
 /* profiling aid: device buffer (2 x 64 int64) that receives clock64() stamps of CTA 0 of the fused attention
  * backward (control thread in row 0, first compute warp in row 1); NULL (default) disables it.        */
 int mfk_debug_set_attn_trace(void* dev_buf);
+/* profiling aid: device buffer (grid x 3 x 64 int64) that receives clock64() stamps of every CTA of the GEMM
+ * (row 0 TMA producer, row 1 MMA issuer, row 2 first epilogue warp; tools/gemm_trace.py); NULL disables it. */
+int mfk_debug_set_gemm_trace(void* dev_buf);
 const char* mfk_error_string(int code);
 
 /* ------------------------------------------------------------------ tensor-core GEMM (tcgen05/TMEM/TMA)
@@ -36,6 +39,10 @@ const char* mfk_error_string(int code);
  *       2: multiply by QuickGELU'(aux[M,N] bf16)   (backward of act 1)
  * N % 32 == 0. tile_n: 0 = auto, 128 or 256 = forced full-tile width, 2 = CTA-pair kernel (cta_group::2, M = 256
  * per pair, each CTA holds half of every B tile).
+ * splitk_ws (optional, NULL = off): device workspace of splitk_ws_bytes (4096 + 148 * 128 KiB covers every shape),
+ * ZERO-FILLED once by the caller and then owned by GEMMs of ONE stream at a time. With it, the tiles of the last
+ * partial wave are cut along K over the idle SMs (fp32 partials summed in fixed slice order: results stay
+ * bit-reproducible). Kernels that use it spin on device-side counters, so two streams must not share one.
  * Replaces: nn.MultiheadAttention in_proj/out_proj (clip/model.py:274,303-305,350), mlp.c_fc +
  * QuickGELU + c_proj (clip/model.py:276-280,162-164,351), conv1 as GEMM (clip/model.py:484,514),
  * `x @ self.proj` (clip/model.py:569-570), `@ self.text_projection` (trainers/maple.py:76), and
@@ -43,7 +50,8 @@ const char* mfk_error_string(int code);
 int mfk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                   const float* bias, int act, const void* aux, long long ldaux, const float* residual,
                   long long ldres, float* out_f32, long long ld32, void* out_bf16, long long ld16,
-                  void* out_pre_bf16, long long ldpre, int tile_n, void* stream);
+                  void* out_pre_bf16, long long ldpre, int tile_n, void* splitk_ws, long long splitk_ws_bytes,
+                  void* stream);
 
 /* out[M,N] fp32 = At^T * Bt, At[K,M] and Bt[K,N] bf16 row-major (MN-major UMMA operands, no transposes).
  * The wgrad form of autograd for the trainable resblocks.11 (trainers/maple.py:472-474,590):

@@ -98,7 +98,7 @@ def test_cabi_library_exports_every_declared_symbol():
     assert b"invalid argument" in lib.mfk_error_string(-1)
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
     assert lib.mfk_gemm_bf16(None, 0, None, 0, 0, 0, 0, None, 0, None, 0, None, 0, None, 0, None, 0, None, 0, 0,
-                             None) == -1
+                             None, 0, None) == -1
 
 
 def test_product_never_imports_oracle():

@@ -75,6 +75,43 @@ def test_gemm_epilogues(M, N, K, tile_n):
     assert (dg.float() - want).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(6368, 768, 3072), (6368, 768, 2304), (12736, 768, 3072), (1000, 800, 3072),
+                                   (3184, 768, 1536)])
+def test_gemm_splitk_tail(M, N, K):
+    """Split-K tail (workspace given): same results as the plain path for every epilogue, bit-reproducible run to
+    run, and the device-side counters re-arm themselves (the workspace is reused without a memset)."""
+    a, b = rnd(M, K, dtype=BF16, seed=7), rnd(N, K, std=K ** -0.5, dtype=BF16, seed=8)
+    bias, res = rnd(N, std=0.1, seed=9), rnd(M, N, seed=10)
+    ws = ops.splitk_workspace(DEV)
+    ref = a.float() @ b.float().t()
+    outs = []
+    for rep in range(3):
+        o32 = torch.full((M, N), float("nan"), device=DEV, dtype=F32)
+        ops.gemm(a, b, bias=bias, residual=res, out_f32=o32, ws=ws)
+        outs.append(o32)
+    torch.cuda.synchronize()
+    assert (ws.view(torch.int32)[:1024] == 0).all()          # counters re-armed
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert (outs[0] - (ref + bias + res)).abs().max().item() < 5e-3
+    plain = torch.empty(M, N, device=DEV, dtype=F32)
+    ops.gemm(a, b, bias=bias, residual=res, out_f32=plain)
+    assert (plain - outs[0]).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    # bf16 output, QuickGELU with saved pre-activation, and its backward, all through the split-K fix-up
+    o16 = torch.empty(M, N, device=DEV, dtype=BF16)
+    ops.gemm(a, b, out_bf16=o16, ws=ws)
+    assert (o16.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+    act = torch.empty(M, N, device=DEV, dtype=BF16)
+    pre = torch.empty(M, N, device=DEV, dtype=BF16)
+    ops.gemm(a, b, bias=bias, act=1, out_bf16=act, out_pre=pre, ws=ws)
+    assert (pre.float() - (ref + bias)).abs().max().item() < 3e-2
+    assert (act.float() - qgelu(pre.float())).abs().max().item() < 2e-2
+    dg = torch.empty(M, N, device=DEV, dtype=BF16)
+    ops.gemm(a, b, act=2, aux=pre, out_bf16=dg, ws=ws)
+    assert (dg.float() - ref * dqgelu(pre.float())).abs().max().item() < 3e-2
+    torch.cuda.synchronize()
+    assert (ws.view(torch.int32)[:1024] == 0).all()
+
+
 def test_gemm_padded_k_operands():
     # wgrad form: operands are transposed copies whose leading dimension is padded to a multiple of 8
     M, N, K, ld = 768, 512, 770, 776

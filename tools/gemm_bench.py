@@ -22,7 +22,8 @@ SHAPES = [  # name, M, N, K, epilogue
     ("text_qkv", 100, 1536, 512, "bias16"),
     ("big_plain", 8192, 8192, 8192, "plain16"),
 ]
-only = sys.argv[1:] 
+only = sys.argv[1:]
+WS = ops.splitk_workspace(dev) if os.environ.get("GB_WS") else None
 flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
 res = {}
 for name, m, n, k, epi in SHAPES:
@@ -36,12 +37,12 @@ for name, m, n, k, epi in SHAPES:
     o32 = torch.empty(m, n, device=dev)
     aux = torch.randn(m, n, device=dev).to(BF16)
     def run():
-        if epi == "bias16": ops.gemm(a, b, bias=bias, out_bf16=o16, k=k, tile_n=TN)
-        elif epi == "plain16": ops.gemm(a, b, out_bf16=o16, k=k, tile_n=TN)
-        elif epi == "plain32": ops.gemm(a, b, out_f32=o32, k=k, tile_n=TN)
-        elif epi == "bias_res32": ops.gemm(a, b, bias=bias, residual=resid, out_f32=o32, k=k, tile_n=TN)
-        elif epi == "gelu": ops.gemm(a, b, bias=bias, act=1, out_bf16=o16, out_pre=o16b, k=k, tile_n=TN)
-        elif epi == "dgelu": ops.gemm(a, b, act=2, aux=aux, out_bf16=o16, k=k, tile_n=TN)
+        if epi == "bias16": ops.gemm(a, b, bias=bias, out_bf16=o16, k=k, tile_n=TN, ws=WS)
+        elif epi == "plain16": ops.gemm(a, b, out_bf16=o16, k=k, tile_n=TN, ws=WS)
+        elif epi == "plain32": ops.gemm(a, b, out_f32=o32, k=k, tile_n=TN, ws=WS)
+        elif epi == "bias_res32": ops.gemm(a, b, bias=bias, residual=resid, out_f32=o32, k=k, tile_n=TN, ws=WS)
+        elif epi == "gelu": ops.gemm(a, b, bias=bias, act=1, out_bf16=o16, out_pre=o16b, k=k, tile_n=TN, ws=WS)
+        elif epi == "dgelu": ops.gemm(a, b, act=2, aux=aux, out_bf16=o16, k=k, tile_n=TN, ws=WS)
     for _ in range(3): run()
     ts = []
     for _ in range(10):
