@@ -1073,6 +1073,8 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   uint64_t* dkv_free = bars + 4;
   uint64_t* unit_free = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_lse = reinterpret_cast<float*>(bars + 8);   // [256] log-sum-exp of the unit's query rows
+  float* s_delta = s_lse + 256;                        // [256] delta = rowsum(dO * O)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = (p.total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -1125,18 +1127,23 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colDP, ad + 2ull * k, bv + 2ull * k, idesc1, k > 0);
         umma_commit(sd_full);
       };
+      const int ks_last = (p.T - (NT - 1) * 128 + 15) / 16;
       int trc_n = 0;
-      for (int u = 0; u < n_units; ++u) {
+      auto issue_loads = [&](int u) {
         const int w = (int)blockIdx.x + u * (int)gridDim.x;
         const int h = w % p.heads, n = w / p.heads;
-        mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
-        TRC(0);  // unit start (previous unit drained)
         mbar_arrive_expect_tx(ld_full, 4u * fullBytes);
         const int row0 = n * p.T;
         tma_load_2d(&tmQkv, ld_full, sQ, h * HD, row0);
         tma_load_2d(&tmQkv, ld_full, sK, D + h * HD, row0);
         tma_load_2d(&tmQkv, ld_full, sV, 2 * D + h * HD, row0);
         tma_load_2d(&tmDo, ld_full, sdO, h * HD, row0);
+      };
+      if (n_units > 0) issue_loads(0);
+      for (int u = 0; u < n_units; ++u) {
+        // the TMEM accumulators of the previous unit must be drained; its loads were issued early (below)
+        mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
+        TRC(0);  // unit start (previous unit drained)
         mbar_wait(ld_full, (uint32_t)u & 1u);
         TRC(0);  // loads landed
         tc_fence_after();
@@ -1146,29 +1153,39 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
           const int j = k / NT, i = k % NT;
           mbar_wait(ds_full, blk_ctr & 1u);
           TRC(0);  // staged operands ready
+          // S/dP of the NEXT block go first: the compute warps have finished reading the S/dP columns, and their
+          // exp / dS arithmetic for block k + 1 then overlaps the second-stage MMAs of block k (they wait for
+          // mma2_done before overwriting the staged P / dS tiles those MMAs read).
+          tc_fence_after();
+          if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
           if (i == 0 && j > 0) {  // accumulators of the previous key tile must have been drained
             mbar_wait(dkv_free, kt_ctr & 1u);
             ++kt_ctr;
+            tc_fence_after();
           }
-          tc_fence_after();
           {
             const uint64_t bdo = dDom + 1024ull * i, bq = dQm + 1024ull * i, bk = dKm + 1024ull * j;
             const uint32_t acc_i = i > 0, acc_j = j > 0;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (K = 128 query rows, 16 per MMA)
+            // reduction depth in 16-row steps: the last query / key tile holds only T - 128 (NT - 1) valid rows
+            // (its staged rows / columns beyond T are zero), so the MMAs over the all-zero tail are not issued.
+            // Plain runtime loops: `#pragma unroll` + `if (ks < n)` around the tcgen05.mma asm miscompiled (nvcc 12.9:
+            // illegal address at run time even with the predicate always true).
+            const int ks_i = i == NT - 1 ? ks_last : 8, ks_j = j == NT - 1 ? ks_last : 8;
+            for (int ks = 0; ks < ks_i; ++ks)  // dV_j += P^T dO_i   (K = query rows of tile i, 16 per MMA)
               umma_bf16(tmem_base + colDV, dPm + 128ull * ks, bdo + 128ull * ks, idesc_tt, acc_i | (ks > 0));
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
+            for (int ks = 0; ks < ks_i; ++ks)  // dK_j += dS^T Q_i
               umma_bf16(tmem_base + colDK, dDsm + 128ull * ks, bq + 128ull * ks, idesc_tt, acc_i | (ks > 0));
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j        (K = 128 keys: 2 column blocks x 4 k-steps)
+            for (int ks = 0; ks < ks_j; ++ks)  // dQ_i += dS K_j        (K = keys of tile j: 2 column blocks x 4 k-steps)
               umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, dDsk + 1024ull * (ks >> 2) + 2ull * (ks & 3),
                         bk + 128ull * ks, idesc_kt, acc_j | (ks > 0));
           }
           umma_commit(mma2_done);
-          if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
           TRC(0);  // second-stage (+ next S/dP) issued
         }
+        // Q, K, V, dO are free once the last block's MMAs have retired: the next unit's loads run under this unit's
+        // epilogue (the compute warps read their accumulators from TMEM and lse / O / dO from global memory)
+        mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
+        if (u + 1 < n_units) issue_loads(u + 1);
         // the last key tile's dkv_free arrive is consumed here so the phase counters stay in step
         mbar_wait(dkv_free, kt_ctr & 1u);
         ++kt_ctr;
@@ -1184,33 +1201,50 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     uint32_t blk_ctr = 0;
     int trc_n = 0;
     const bool trc_me = warp == 0 && lane == 0;
-    for (int u = 0; u < n_units; ++u) {
+    // lse and delta = rowsum(dO * O) of the unit's query rows -> smem. Coalesced: this warp owns 32 of the (<= 256)
+    // rows; 8 lanes read the 128 bytes of one (row, head) of O and of dO, 4 rows per instruction, and the row dot
+    // product is finished with 3 shuffles (one lane per row reading its own 128 bytes would cost 32 memory
+    // wavefronts per instruction instead of 4).
+    auto row_stats = [&](int u) {
       const int w = (int)blockIdx.x + u * (int)gridDim.x;
       const int h = w % p.heads, n = w / p.heads;
       const size_t sidx = ((size_t)n * p.heads + h) * p.T;
-      // lse and delta = rowsum(dO * O) of this thread's query row in both query tiles: fetched up front, while the
-      // control thread is still waiting for the unit's TMA loads
-      float Lc[2] = {0.f, 0.f}, dcache[2] = {0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int qrow = i * 128 + rl;
-        if (i < NT && qrow < p.T) {
-          Lc[i] = p.lse[sidx + qrow];
-          const size_t off = ((size_t)n * p.T + qrow) * D + h * HD;
-          const uint4* po = reinterpret_cast<const uint4*>(p.out + off);
-          const uint4* pd = reinterpret_cast<const uint4*>(p.d_out + off);
-          float dsum = 0.f;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint4 a = __ldg(po + t), b = __ldg(pd + t);
-            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-            const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
-            dsum += (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
-                    (a3.x * b3.x + a3.y * b3.y);
-          }
-          dcache[i] = dsum;
-        }
+      const int r0 = warp * 32;
+      {
+        const int qrow = r0 + lane;
+        s_lse[qrow] = qrow < p.T ? p.lse[sidx + qrow] : 0.f;
       }
+      // all 16 loads are issued before the first use (one memory round trip instead of eight)
+      uint4 va[8], vb[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int qrow = min(r0 + g * 4 + (lane >> 3), p.T - 1);  // clamped: rows >= T are discarded below
+        const size_t off = ((size_t)n * p.T + qrow) * D + h * HD + (lane & 7) * 8;
+        va[g] = __ldg(reinterpret_cast<const uint4*>(p.out + off));
+        vb[g] = __ldg(reinterpret_cast<const uint4*>(p.d_out + off));
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int qrow = r0 + g * 4 + (lane >> 3);
+        const uint4 a = va[g], b = vb[g];
+        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+        const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+        float dsum = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
+                     (a3.x * b3.x + a3.y * b3.y);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+        if ((lane & 7) == 0) s_delta[qrow] = qrow < p.T ? dsum : 0.f;
+      }
+    };
+    // The first unit's are fetched up front (under its TMA loads); those of unit u + 1 inside unit u's last block,
+    // where this warp would otherwise idle waiting for the second-stage MMAs.
+    if (n_units > 0) row_stats(0);
+    for (int u = 0; u < n_units; ++u) {
+      const int w = (int)blockIdx.x + u * (int)gridDim.x;
+      const int h = w % p.heads, n = w / p.heads;
+      asm volatile("bar.sync 2, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");  // row stats of this unit are in smem
+      const float Lc[2] = {s_lse[rl], s_lse[128 + rl]}, dcache[2] = {s_delta[rl], s_delta[128 + rl]};
       for (int k = 0; k < nblk; ++k, ++blk_ctr) {
         const int j = k / NT, i = k % NT;
         const int qrow = i * 128 + rl;
@@ -1218,7 +1252,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         const float L = i == 0 ? Lc[0] : Lc[1];
         const float Dl = i == 0 ? dcache[0] : dcache[1];
         if (trc_me) TRC(1);  // about to wait for S/dP
-        mbar_wait(sd_full, blk_ctr & 1u);  // also implies the previous block's second-stage MMAs retired
+        mbar_wait(sd_full, blk_ctr & 1u);
         if (trc_me) TRC(1);  // S/dP ready
         tc_fence_after();
 #pragma unroll
@@ -1240,6 +1274,9 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
           }
           const uint32_t boff = (uint32_t)(c >> 6) * 16384u;
           const uint32_t ch0 = (uint32_t)(c & 63) >> 3;
+          // the staged P / dS tiles are still being read by the previous block's second-stage MMAs (which now run
+          // concurrently with the arithmetic above): wait for them before the first store of this block
+          if (cc == 0 && blk_ctr > 0) mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const uint32_t off = boff + (((ch0 + t) ^ x7) << 4);
@@ -1258,53 +1295,57 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
         if (trc_me) TRC(1);  // staged
+        if (k == nblk - 1 && u + 1 < n_units) row_stats(u + 1);  // (every thread read this unit's at its start)
         if (i == NT - 1) {
           // ---- key tile j complete: dK_j (scaled), dV_j -> global
           mbar_wait(mma2_done, blk_ctr & 1u);
           if (trc_me) TRC(1);  // second-stage done
           tc_fence_after();
-          const int key = j * 128 + rl;
-          const size_t grow = ((size_t)n * p.T + key) * (3 * (size_t)D) + h * HD + half * 32;
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
+          // Accumulators -> bf16 tiles staged in the (now idle) P / dS buffers -> coalesced global stores: a thread
+          // owns one TMEM lane (= row), and 32 lanes storing 64 bytes of 32 different rows each cost 32 memory
+          // wavefronts per instruction; from the staged tile a warp instruction writes 4 whole 128-byte rows.
+          // Tiles: 0 dK_j, 1 dV_j (sP), 2.. dQ_i (sdS, last key tile only). 16-byte chunks XOR-swizzled by row.
+          const int ntile = (j == NT - 1) ? 2 + NT : 2;
+          auto stage_tile = [&](int tile, uint32_t col, float sc) {
             uint32_t r[32];
-            tmem_ld32(tlane + (part == 0 ? colDK : colDV) + (uint32_t)(half * 32), r);
+            tmem_ld32(tlane + col + (uint32_t)(half * 32), r);
             tc_wait_ld();
-            if (key < p.T) {
-              const float sc = part == 0 ? p.scale : 1.f;
-              bf16* dst = p.dqkv + grow + (part == 0 ? D : 2 * D);
+            const uint32_t base = smem_u32(sP) + (uint32_t)tile * 16384u + (uint32_t)rl * 128u;
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 4; ++t)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((((uint32_t)half * 4 + t) ^ x7) << 4)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t]) * sc, __uint_as_float(r[8 * t + 1]) * sc)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t + 2]) * sc, __uint_as_float(r[8 * t + 3]) * sc)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t + 4]) * sc, __uint_as_float(r[8 * t + 5]) * sc)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t + 6]) * sc, __uint_as_float(r[8 * t + 7]) * sc))
+                           : "memory");
+          };
+          stage_tile(0, colDK, p.scale);
+          stage_tile(1, colDV, 1.f);
+          if (j == NT - 1)
+            for (int ii = 0; ii < NT; ++ii) stage_tile(2 + ii, colDQ + (uint32_t)ii * 64u, p.scale);
+          asm volatile("bar.sync 3, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
+          for (int tile = 0; tile < ntile; ++tile) {
+            // tile rows are keys of tile j (dK, dV) or queries of tile (tile - 2); column offset 0 q | D k | 2D v
+            const int seq0 = tile < 2 ? j * 128 : (tile - 2) * 128;
+            const int coff = tile == 0 ? D : tile == 1 ? 2 * D : 0;
+            const uint32_t tbase = smem_u32(sP) + (uint32_t)tile * 16384u;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int idx = (int)threadIdx.x + m * (TC_SOFTMAX_WARPS * 32);
+              const int row = idx >> 3, ch = idx & 7;
+              if (seq0 + row < p.T) {
                 uint4 v;
-                v.x = pack_bf16(__uint_as_float(r[8 * t]) * sc, __uint_as_float(r[8 * t + 1]) * sc);
-                v.y = pack_bf16(__uint_as_float(r[8 * t + 2]) * sc, __uint_as_float(r[8 * t + 3]) * sc);
-                v.z = pack_bf16(__uint_as_float(r[8 * t + 4]) * sc, __uint_as_float(r[8 * t + 5]) * sc);
-                v.w = pack_bf16(__uint_as_float(r[8 * t + 6]) * sc, __uint_as_float(r[8 * t + 7]) * sc);
-                *reinterpret_cast<uint4*>(dst + 8 * t) = v;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(tbase + (uint32_t)row * 128u + (((uint32_t)ch ^ ((uint32_t)row & 7u)) << 4)));
+                *reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.T + seq0 + row) * (3 * (size_t)D) + coff + h * HD +
+                                          ch * 8) = v;
               }
             }
           }
-          if (j == NT - 1) {
-            // ---- unit complete: dQ_i (scaled) -> global
-            for (int ii = 0; ii < NT; ++ii) {
-              uint32_t r[32];
-              tmem_ld32(tlane + colDQ + (uint32_t)ii * 64u + (uint32_t)(half * 32), r);
-              tc_wait_ld();
-              const int qr = ii * 128 + rl;
-              if (qr < p.T) {
-                bf16* dst = p.dqkv + ((size_t)n * p.T + qr) * (3 * (size_t)D) + h * HD + half * 32;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  uint4 v;
-                  v.x = pack_bf16(__uint_as_float(r[8 * t]) * p.scale, __uint_as_float(r[8 * t + 1]) * p.scale);
-                  v.y = pack_bf16(__uint_as_float(r[8 * t + 2]) * p.scale, __uint_as_float(r[8 * t + 3]) * p.scale);
-                  v.z = pack_bf16(__uint_as_float(r[8 * t + 4]) * p.scale, __uint_as_float(r[8 * t + 5]) * p.scale);
-                  v.w = pack_bf16(__uint_as_float(r[8 * t + 6]) * p.scale, __uint_as_float(r[8 * t + 7]) * p.scale);
-                  *reinterpret_cast<uint4*>(dst + 8 * t) = v;
-                }
-              }
-            }
-          }
+          // the staged tiles are overwritten by the next block's P / dS: every thread must have read them
+          asm volatile("bar.sync 3, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
           tc_fence_before();
           __syncwarp();
           if (trc_me) TRC(1);  // epilogue stores issued
@@ -1358,7 +1399,7 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   int rc;
   if ((rc = mfk_make_tmap_2d(&tmQkv, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;
   if ((rc = mfk_make_tmap_2d(&tmDo, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;
-  const size_t smem = 4 * (size_t)p.R * 128 + 65536 + 128 + 1024;
+  const size_t smem = 4 * (size_t)p.R * 128 + 65536 + 128 + 2048 + 1024;
   e = cudaFuncSetAttribute(attn_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.total_units < g_attn_sms ? p.total_units : g_attn_sms;
