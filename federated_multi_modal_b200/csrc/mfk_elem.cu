@@ -460,6 +460,86 @@ __global__ void linear_small_bwd_x_kernel(const float* __restrict__ W, const flo
   }
 }
 
+
+// ---- grouped forms: ONE launch for all prompt-learner projections of a step (9 forward problems, 9 backward
+// problems with m = n_ctx rows): the per-launch latency of 27 tiny kernels was a visible slice of the step's serial
+// head and tail. The problem table lives in device memory (pointers into the parameter / gradient arenas are stable).
+struct SmallLinearProblem {  // mirrors mfk.h
+  const float* x; const float* W; const float* b; float* y;
+  const float* dy; float* dW; float* db; const float* dx_add; float* dx;
+  int m, N, K, pad;
+};
+__global__ void linear_small_fwd_grouped_kernel(const SmallLinearProblem* __restrict__ tab) {
+  const SmallLinearProblem pr = tab[blockIdx.y];
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= pr.N) return;
+  for (int r = 0; r < pr.m; ++r) {
+    float s = 0.f;
+    for (int k = lane; k < pr.K; k += 32) s += pr.x[(size_t)r * pr.K + k] * pr.W[(size_t)n * pr.K + k];
+    s = warp_sum(s);
+    if (lane == 0) pr.y[(size_t)r * pr.N + n] = s + (pr.b ? pr.b[n] : 0.f);
+  }
+}
+__global__ void linear_small_bwd_w_grouped_kernel(const SmallLinearProblem* __restrict__ tab) {
+  const SmallLinearProblem pr = tab[blockIdx.y];
+  const int n = blockIdx.x;
+  if (n >= pr.N || !pr.dW) return;
+  for (int k = threadIdx.x; k < pr.K; k += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < pr.m; ++r) s += pr.dy[(size_t)r * pr.N + n] * pr.x[(size_t)r * pr.K + k];
+    pr.dW[(size_t)n * pr.K + k] = s;
+  }
+  if (threadIdx.x == 0 && pr.db) {
+    float s = 0.f;
+    for (int r = 0; r < pr.m; ++r) s += pr.dy[(size_t)r * pr.N + n];
+    pr.db[n] = s;
+  }
+}
+// grid (ceil(maxK/32), max m, problems), block (32, 32): same reduction order as linear_small_bwd_x_kernel
+__global__ void linear_small_bwd_x_grouped_kernel(const SmallLinearProblem* __restrict__ tab) {
+  __shared__ float red[32][33];
+  const SmallLinearProblem pr = tab[blockIdx.z];
+  const int k = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y;
+  if (r >= pr.m || !pr.dx || blockIdx.x * 32 >= pr.K) return;  // uniform per block
+  float s = 0.f;
+  if (k < pr.K)
+    for (int n = threadIdx.y; n < pr.N; n += 32) s += pr.dy[(size_t)r * pr.N + n] * pr.W[(size_t)n * pr.K + k];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < pr.K) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += red[w][threadIdx.x];
+    pr.dx[(size_t)r * pr.K + k] = t + (pr.dx_add ? pr.dx_add[(size_t)r * pr.K + k] : 0.f);
+  }
+}
+
+// ---- grouped fp32 [M,N] -> bf16 copy + bf16 transpose (refresh of the trainable block weights after an update)
+struct RepackProblem {  // mirrors mfk.h
+  const float* in; bf16* out_t; bf16* copy; int M, N;
+};
+__global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab) {
+  __shared__ float tile[32][33];
+  const RepackProblem pr = tab[blockIdx.z];
+  const int n0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  if (n0 >= pr.N || m0 >= pr.M) return;  // uniform per block
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = m0 + i, n = n0 + threadIdx.x;
+    float v = 0.f;
+    if (m < pr.M && n < pr.N) {
+      v = pr.in[(size_t)m * pr.N + n];
+      if (pr.copy) pr.copy[(size_t)m * pr.N + n] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, m = m0 + threadIdx.x;
+    if (n < pr.N && m < pr.M) pr.out_t[(size_t)n * pr.M + m] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
 }  // namespace
 
 // ================================================================================ C ABI
@@ -634,6 +714,32 @@ extern "C" int mfk_linear_small_bwd(const float* x, const float* W, const float*
   if (!x || !W || !dy || m <= 0) return MFK_EARG;
   if (dW) linear_small_bwd_w_kernel<<<N, 128, 0, ST(stream)>>>(x, dy, dW, db, m, N, K);
   if (dx) linear_small_bwd_x_kernel<<<dim3((K + 31) / 32, m), dim3(32, 32), 0, ST(stream)>>>(W, dy, dx_add, dx, m, N, K);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_linear_small_fwd_grouped(const void* problems_dev, int n_problems, int max_N, void* stream) {
+  if (!problems_dev || n_problems <= 0 || max_N <= 0) return MFK_EARG;
+  linear_small_fwd_grouped_kernel<<<dim3((max_N + 7) / 8, n_problems), 256, 0, ST(stream)>>>(
+      static_cast<const SmallLinearProblem*>(problems_dev));
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_linear_small_bwd_grouped(const void* problems_dev, int n_problems, int max_m, int max_N, int max_K,
+                                            void* stream) {
+  if (!problems_dev || n_problems <= 0 || max_m <= 0 || max_N <= 0 || max_K <= 0) return MFK_EARG;
+  const SmallLinearProblem* tab = static_cast<const SmallLinearProblem*>(problems_dev);
+  linear_small_bwd_w_grouped_kernel<<<dim3(max_N, n_problems), 128, 0, ST(stream)>>>(tab);
+  linear_small_bwd_x_grouped_kernel<<<dim3((max_K + 31) / 32, max_m, n_problems), dim3(32, 32), 0, ST(stream)>>>(tab);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_repack_grouped(const void* problems_dev, int n_problems, int max_M, int max_N, void* stream) {
+  if (!problems_dev || n_problems <= 0 || max_M <= 0 || max_N <= 0) return MFK_EARG;
+  repack_grouped_kernel<<<dim3((max_N + 31) / 32, (max_M + 31) / 32, n_problems), dim3(32, 8), 0, ST(stream)>>>(
+      static_cast<const RepackProblem*>(problems_dev));
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

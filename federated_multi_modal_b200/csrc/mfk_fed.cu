@@ -106,9 +106,16 @@ __global__ void check_finite_kernel(const TIN* __restrict__ p, long long n, int*
 // ---------------------------------------------------------------------------- clip_grad_norm_ + SGD
 __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
   __shared__ float red[8];
-  float s = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    s += g[i] * g[i];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    s0 += v.x * v.x; s1 += v.y * v.y; s2 += v.z * v.z; s3 += v.w * v.w;
+  }
+  float s = (s0 + s1) + (s2 + s3);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) s += g[i] * g[i];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -133,17 +140,29 @@ __global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, fl
   const bool nesterov = hp[5] != 0.f, first = hp[6] != 0.f;
   float coef = 1.f;
   if (max_norm > 0.f) coef = fminf(max_norm / (total_norm[0] + 1e-6f), 1.f);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gc = g[i] * coef;
-    g[i] = gc;  // grads are clipped in place, as clip_grad_norm_ does
-    float d = gc + wd * p[i];
+  auto upd = [&](float& pv, float& gv, float& mv) {
+    const float gc = gv * coef;
+    gv = gc;  // grads are clipped in place, as clip_grad_norm_ does
+    float d = gc + wd * pv;
     if (mu != 0.f) {
-      const float b = first ? d : mu * mom[i] + (1.f - damp) * d;
-      mom[i] = b;
+      const float b = first ? d : mu * mv + (1.f - damp) * d;
+      mv = b;
       d = nesterov ? d + mu * b : b;
     }
-    p[i] -= lr * d;
+    pv -= lr * d;
+  };
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(mom);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = p4[i], gv = g4[i], mv = (mu != 0.f && !first) ? m4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    upd(pv.x, gv.x, mv.x); upd(pv.y, gv.y, mv.y); upd(pv.z, gv.z, mv.z); upd(pv.w, gv.w, mv.w);
+    p4[i] = pv; g4[i] = gv;
+    if (mu != 0.f) m4[i] = mv;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) upd(p[i], g[i], mom[i]);
 }
 
 }  // namespace
@@ -179,6 +198,7 @@ extern "C" int mfk_check_finite(const void* p, long long n, int dtype, int* flag
 
 extern "C" int mfk_grad_norm(const float* g, long long n, float* partial_ws, float* norm_out, void* stream) {
   if (!g || n <= 0 || !partial_ws || !norm_out) return MFK_EARG;
+  if (!mfk_aligned16(g)) return MFK_EALIGN;
   const int P = 296;
   sumsq_partial_kernel<<<P, 256, 0, ST(stream)>>>(g, n, partial_ws);
   sumsq_final_kernel<<<1, 32, 0, ST(stream)>>>(partial_ws, P, norm_out);
@@ -189,7 +209,9 @@ extern "C" int mfk_grad_norm(const float* g, long long n, float* partial_ws, flo
 extern "C" int mfk_sgd_step(float* p, float* g, float* mom, long long n, const float* hyper_dev,
                             const float* total_norm_dev, void* stream) {
   if (!p || !g || !mom || n <= 0 || !hyper_dev || !total_norm_dev) return MFK_EARG;
-  long long blocks = (n + 255) / 256;
+  if (!mfk_aligned16(p) || !mfk_aligned16(g) || !mfk_aligned16(mom)) return MFK_EALIGN;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   sgd_step_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(p, g, mom, n, hyper_dev, total_norm_dev);
   MFK_CHECK_LAUNCH();

@@ -190,12 +190,15 @@ class MapleEngine:
         return torch.cat([hi, hi, lo], dim=1).contiguous()
 
     def repack_trainable(self):
-        """Refresh the bf16 (and transposed) copies of the trainable resblock weights from the fp32 arena."""
-        for tw in (self.vis, self.txt):
-            for w in tw.w:
-                for lin in _LIN:
-                    if lin + ".master" in w:
-                        ops.transpose_bf16(w[lin + ".master"], w[lin + ".wT"], w[lin + ".w"])
+        """Refresh the bf16 (and transposed) copies of the trainable resblock weights from the fp32 arena: one
+        grouped launch over all of them."""
+        if getattr(self, "_repack_table", None) is None:
+            probs = [(w[lin + ".master"], w[lin + ".wT"], w[lin + ".w"]) for tw in (self.vis, self.txt) for w in tw.w
+                     for lin in _LIN if lin + ".master" in w]
+            self._repack_table = ops.repack_table(probs, self.dev) if probs else False
+            self._repack_max = (max(m.shape[0] for m, _, _ in probs), max(m.shape[1] for m, _, _ in probs)) if probs else (0, 0)
+        if self._repack_table is not False:
+            ops.repack_grouped(self._repack_table, *self._repack_max)
         self._text_cache_valid = False
 
     # ------------------------------------------------------------------ workspaces
@@ -259,28 +262,45 @@ class MapleEngine:
             ws["csum"] = b("csum", (32 * 4 * D,), F32)
 
     # ------------------------------------------------------------------ prompt learner
-    def _prompt_learner_fwd(self):
-        p, nd = self.p, self.J - 1
+    def _prompt_learner_problems(self):
+        """The J-1 compound projections + proj_lang_to_vis as one problem table (forward AND backward pointers).
+        Everything it points to (arena slices, persistent workspaces) keeps its address for the engine's life."""
+        p, G, nd, n = self.p, self.g, self.J - 1, self.n
         pl = "prompt_learner."
         self.deep_text: List[torch.Tensor] = []
         self.deep_vis: List[torch.Tensor] = []
+        probs = []
+        dpr = lambda tw, i: self._buf(f"{tw.name}.dprompt{i}", (n, tw.D), F32)
         for i in range(nd):
-            W, b = p[f"{pl}compound_prompt_projections.{i}.weight"], p[f"{pl}compound_prompt_projections.{i}.bias"]
-            if i % 2 == 0:
-                t = p[f"{pl}compound_prompts_text_parameters.{i // 2}"]
-                y = self._buf(f"pl.y{i}", (self.n, W.shape[0]), F32)
-                ops.linear_small_fwd(t, W, b, y)
+            Wn = f"{pl}compound_prompt_projections.{i}"
+            W, b = p[Wn + ".weight"], p[Wn + ".bias"]
+            y = self._buf(f"pl.y{i}", (n, W.shape[0]), F32)
+            if i % 2 == 0:   # text parameter -> vision prompt; dx = dy W + d(text prompt i)
+                pn = f"{pl}compound_prompts_text_parameters.{i // 2}"
                 self.deep_vis.append(y)
-                self.deep_text.append(t)
-            else:
-                v = p[f"{pl}visual_deep_prompts_parameters.{(i - 1) // 2}"]
-                y = self._buf(f"pl.y{i}", (self.n, W.shape[0]), F32)
-                ops.linear_small_fwd(v, W, b, y)
+                self.deep_text.append(p[pn])
+                dy, dx_add = dpr(self.vis, i), dpr(self.txt, i)
+            else:            # vision parameter -> text prompt
+                pn = f"{pl}visual_deep_prompts_parameters.{(i - 1) // 2}"
                 self.deep_text.append(y)
-                self.deep_vis.append(v)
-        self.shared = self._buf("pl.shared", (self.n, self.vis.D), F32)
-        ops.linear_small_fwd(p[pl + "ctx"], p[pl + "proj_lang_to_vis.weight"], p[pl + "proj_lang_to_vis.bias"],
-                             self.shared)
+                self.deep_vis.append(p[pn])
+                dy, dx_add = dpr(self.txt, i), dpr(self.vis, i)
+            probs.append(dict(x=p[pn], W=W, b=b, y=y, dy=dy, dW=G[Wn + ".weight"], db=G[Wn + ".bias"], dx_add=dx_add,
+                              dx=G[pn]))
+        self.shared = self._buf("pl.shared", (n, self.vis.D), F32)
+        self.d_shared = self._buf("pl.dshared", (n, self.vis.D), F32)
+        self.d_ctx_t = self._buf("pl.dctx_t", (n, self.txt.D), F32)
+        probs.append(dict(x=p[pl + "ctx"], W=p[pl + "proj_lang_to_vis.weight"], b=p[pl + "proj_lang_to_vis.bias"],
+                          y=self.shared, dy=self.d_shared, dW=G[pl + "proj_lang_to_vis.weight"],
+                          db=G[pl + "proj_lang_to_vis.bias"], dx_add=self.d_ctx_t, dx=G[pl + "ctx"]))
+        self._pl_table = ops.small_linear_table(probs, self.dev)
+        self._pl_keep = probs  # fixed-size buffers: _buf never reallocates them, so the pointers stay valid
+
+    def _prompt_learner_fwd(self):
+        """MultiModalPromptLearner.forward (trainers/maple.py:194-215): all projections in one grouped launch."""
+        if getattr(self, "_pl_table", None) is None:
+            self._prompt_learner_problems()
+        ops.linear_small_fwd_grouped(self._pl_table, max(self.vis.D, self.txt.D))
 
     # ------------------------------------------------------------------ one residual block
     def _slots(self, l: int, train: bool):
@@ -563,33 +583,19 @@ class MapleEngine:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             dt = self._tower_bwd(self.txt, dft, self.tproj, txs, tstat, self.txt_rows, "text_encoder.ln_final", C, 1)
-            d_ctx_t = self._buf("pl.dctx_t", (n, self.txt.D), F32)
-            ops.prompt_splice_bwd(self.txt.ws["g"], None, d_ctx_t, C, self.Te, 1, n, False, False)
+            ops.prompt_splice_bwd(self.txt.ws["g"], None, self.d_ctx_t, C, self.Te, 1, n, False, False)
         dv = self._tower_bwd(self.vis, dfi, self.vproj, vxs, vstat, self.cls_rows, "image_encoder.ln_post", B,
                              self.Tv - n)
         vws = self.vis.ws
         ops.layernorm_bwd(vws["g"], self.vx0, self.vstat0[0], self.vstat0[1], p["image_encoder.ln_pre.weight"],
                           g_out=vws["g"], dgamma=G["image_encoder.ln_pre.weight"] if ln_grads else None,
                           dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None, partial_ws=vws["lnp"])
-        d_shared = self._buf("pl.dshared", (n, self.vis.D), F32)
-        ops.prompt_splice_bwd(vws["g"], None, d_shared, B, self.Tv, self.Tv - n, n, True, False)
+        ops.prompt_splice_bwd(vws["g"], None, self.d_shared, B, self.Tv, self.Tv - n, n, True, False)
         main.wait_stream(side)
 
-        # ---- prompt learner backward
-        pl = "prompt_learner."
-        for i in range(nd):
-            Wn = f"{pl}compound_prompt_projections.{i}"
-            if i % 2 == 0:
-                pn = f"{pl}compound_prompts_text_parameters.{i // 2}"
-                ops.linear_small_bwd(p[pn], p[Wn + ".weight"], dv[i], dW=G[Wn + ".weight"], db=G[Wn + ".bias"],
-                                     dx_add=dt[i], dx=G[pn])
-            else:
-                pn = f"{pl}visual_deep_prompts_parameters.{(i - 1) // 2}"
-                ops.linear_small_bwd(p[pn], p[Wn + ".weight"], dt[i], dW=G[Wn + ".weight"], db=G[Wn + ".bias"],
-                                     dx_add=dv[i], dx=G[pn])
-        ops.linear_small_bwd(p[pl + "ctx"], p[pl + "proj_lang_to_vis.weight"], d_shared,
-                             dW=G[pl + "proj_lang_to_vis.weight"], db=G[pl + "proj_lang_to_vis.bias"],
-                             dx_add=d_ctx_t, dx=G[pl + "ctx"])
+        # ---- prompt learner backward: dW, db and dx = dy W + d(prompt) for all projections in
+        # two grouped launches (the problem table was built with the forward one)
+        ops.linear_small_bwd_grouped(self._pl_table, n, max(self.vis.D, self.txt.D), max(self.vis.D, self.txt.D))
         self.last = dict(image_features=fi, text_features=ft, dfi=dfi, dft=dft)
         return loss, logits
 

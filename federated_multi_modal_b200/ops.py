@@ -156,6 +156,35 @@ def linear_small_bwd(x, W, dy, *, dW=None, db=None, dx_add=None, dx=None):
          kernels=(dW is not None) + (dx is not None))
 
 
+def small_linear_table(problems, device) -> torch.Tensor:
+    """Device table of mfk_small_linear_problem (see mfk.h) from dicts with tensors x, W, b, y, dy, dW, db, dx_add,
+    dx (missing / None -> NULL). Pointers are captured: the tensors must stay alive and in place."""
+    rows = []
+    for pr in problems:
+        ptr = lambda k: (pr[k].data_ptr() if pr.get(k) is not None else 0)
+        m, (N, K) = pr["x"].shape[0], pr["W"].shape
+        rows.append([ptr(k) for k in ("x", "W", "b", "y", "dy", "dW", "db", "dx_add", "dx")] + [m | (N << 32), K])
+    return torch.tensor(rows, dtype=torch.int64, device=device).contiguous()
+
+
+def linear_small_fwd_grouped(table, max_N):
+    call("mfk_linear_small_fwd_grouped", table, table.shape[0], max_N, stream_ptr())
+
+
+def linear_small_bwd_grouped(table, max_m, max_N, max_K):
+    call("mfk_linear_small_bwd_grouped", table, table.shape[0], max_m, max_N, max_K, stream_ptr(), kernels=2)
+
+
+def repack_table(problems, device) -> torch.Tensor:
+    """Device table of mfk_repack_problem from (master fp32 [M,N], out_t bf16 [N,M], copy bf16 [M,N]) triples."""
+    rows = [[w.data_ptr(), t.data_ptr(), c.data_ptr(), w.shape[0] | (w.shape[1] << 32)] for w, t, c in problems]
+    return torch.tensor(rows, dtype=torch.int64, device=device).contiguous()
+
+
+def repack_grouped(table, max_M, max_N):
+    call("mfk_repack_grouped", table, table.shape[0], max_M, max_N, stream_ptr())
+
+
 def head_workspace_floats(B, C, E) -> int:
     return call("mfk_head_workspace_floats", B, C, E)
 

@@ -136,6 +136,23 @@ int mfk_linear_small_fwd(const float* x, const float* W, const float* b, float* 
                          void* stream);
 int mfk_linear_small_bwd(const float* x, const float* W, const float* dy, float* dW, float* db,
                          const float* dx_add, float* dx, int m, int N, int K, void* stream);
+/* Grouped forms: ONE launch (two for the backward: dW/db, dx) over a DEVICE table of problems — all J-1 compound
+ * projections + proj_lang_to_vis of a step (trainers/maple.py:194-215). Unused outputs are NULL. Same arithmetic
+ * and reduction order as the single-problem calls.                                                     */
+typedef struct mfk_small_linear_problem {
+  const float* x; const float* W; const float* b; float* y;                  /* forward:  y = x W^T + b          */
+  const float* dy; float* dW; float* db; const float* dx_add; float* dx;     /* backward: dW, db, dx = dy W + add */
+  int m, N, K, pad;
+} mfk_small_linear_problem;
+int mfk_linear_small_fwd_grouped(const void* problems_dev, int n_problems, int max_N, void* stream);
+int mfk_linear_small_bwd_grouped(const void* problems_dev, int n_problems, int max_m, int max_N, int max_K,
+                                 void* stream);
+/* Grouped refresh of the bf16 copies of trainable fp32 weights after an optimiser step (one launch):
+ * copy[M,N] = bf16(in), out_t[N,M] = bf16(in)^T (the K-major operand of the dgrad GEMM).               */
+typedef struct mfk_repack_problem {
+  const float* in; void* out_t; void* copy; int M, N;
+} mfk_repack_problem;
+int mfk_repack_grouped(const void* problems_dev, int n_problems, int max_M, int max_N, void* stream);
 
 /* ------------------------------------------------------------------ logits + loss head (trainers/maple.py:325-372)
  * label == NULL: inference, only `logits` [B,C] is written. Otherwise also loss[1], d_img[B,E], d_txt[C,E].

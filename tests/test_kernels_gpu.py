@@ -304,6 +304,34 @@ def test_small_linear():
     assert (dx - (dy @ W + add)).abs().max().item() < 1e-3
 
 
+def test_grouped_small_linear_and_repack_match_single_calls():
+    probs, ref = [], []
+    for i, (N, K) in enumerate([(768, 512), (512, 768), (768, 512)]):
+        x, W, b = rnd(2, K, seed=20 + i), rnd(N, K, std=0.02, seed=30 + i), rnd(N, std=0.1, seed=40 + i)
+        dy, add = rnd(2, N, seed=50 + i), rnd(2, K, seed=60 + i)
+        y, dW, db, dx = (torch.empty(2, N, device=DEV), torch.empty(N, K, device=DEV), torch.empty(N, device=DEV),
+                         torch.empty(2, K, device=DEV))
+        probs.append(dict(x=x, W=W, b=b, y=y, dy=dy, dW=dW, db=db, dx_add=add, dx=dx))
+        y1, dW1, db1, dx1 = torch.empty_like(y), torch.empty_like(dW), torch.empty_like(db), torch.empty_like(dx)
+        ops.linear_small_fwd(x, W, b, y1)
+        ops.linear_small_bwd(x, W, dy, dW=dW1, db=db1, dx_add=add, dx=dx1)
+        ref.append((y1, dW1, db1, dx1))
+    tab = ops.small_linear_table(probs, DEV)
+    ops.linear_small_fwd_grouped(tab, 768)
+    ops.linear_small_bwd_grouped(tab, 2, 768, 768)
+    torch.cuda.synchronize()
+    for pr, (y1, dW1, db1, dx1) in zip(probs, ref):   # same arithmetic and reduction order: bit-identical
+        assert torch.equal(pr["y"], y1) and torch.equal(pr["dW"], dW1)
+        assert torch.equal(pr["db"], db1) and torch.equal(pr["dx"], dx1)
+    # grouped repack == transpose_bf16 per matrix
+    ws = [rnd(96, 160, seed=70), rnd(512, 2048, seed=71)]
+    trip = [(w, torch.empty(w.shape[1], w.shape[0], device=DEV, dtype=BF16),
+             torch.empty(w.shape, device=DEV, dtype=BF16)) for w in ws]
+    ops.repack_grouped(ops.repack_table(trip, DEV), 512, 2048)
+    for w, t, c in trip:
+        assert torch.equal(c, w.to(BF16)) and torch.equal(t, w.to(BF16).t().contiguous())
+
+
 @pytest.mark.parametrize("B,C", [(4, 10), (32, 38), (32, 1000)])
 def test_head(B, C):
     E = 512

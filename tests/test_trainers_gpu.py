@@ -89,6 +89,23 @@ def test_maple_forward_backward_graph_equals_eager_and_learns():
                        t.model.engine.p["prompt_learner.compound_prompts_text_parameters.0"])
 
 
+def test_training_is_bit_reproducible_at_bench_batch():
+    """Batch 32 (M = 6368 rows: split-K GEMM tails, multi-unit attention CTAs): two independent trainers fed the
+    same batches end with bit-identical gradients and parameters — no atomics / races / uninitialised reads."""
+    batches = [synth.make_batch(32, 10, 7 + i) for i in range(2)]
+    outs = []
+    for rep in range(2):
+        t = _trainer(False)
+        t.model.train()
+        for i in range(3):
+            img, lab = batches[i % 2]
+            t.forward_backward({"img": img.pin_memory(), "label": lab.pin_memory()})
+        torch.cuda.synchronize()
+        outs.append((t.model.engine.grads.clone(), t.model.engine.params.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 def test_maple_rejects_bad_input_like_reference():
     t = _trainer(False)
     img, lab = synth.make_batch(4, 10, 123)
