@@ -515,6 +515,34 @@ __global__ void linear_small_bwd_x_grouped_kernel(const SmallLinearProblem* __re
   }
 }
 
+// ---- grouped second stage of the LayerNorm dgamma / dbeta reductions: the per-CTA partials of every LayerNorm
+// backward of a tower are reduced by ONE launch at the end of the tower (the 4.5 us dependent launch after each
+// of the 26 LayerNorm backwards sat on the critical path). Same summation order as partial_reduce_kernel.
+struct PartialReduceProblem {  // mirrors mfk.h
+  const float* partial; int P, N; float* out0; float* out1; int accumulate, pad;
+};
+__global__ void partial_reduce_grouped_kernel(const PartialReduceProblem* __restrict__ tab) {
+  __shared__ float red[32][33];
+  pdl_trigger();
+  pdl_wait();  // launched with the PDL attribute: the LayerNorm backwards before it must have completed
+  const PartialReduceProblem pr = tab[blockIdx.z];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x * 32 >= pr.N) return;  // uniform per block
+  float* out = blockIdx.y == 0 ? pr.out0 : pr.out1;
+  const float* src = pr.partial + (size_t)blockIdx.y * pr.N;
+  float s = 0.f;
+  if (c < pr.N && out)
+    for (int p = threadIdx.y; p < pr.P; p += 32) s += src[(size_t)p * 2 * pr.N + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < pr.N && out) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += red[w][threadIdx.x];
+    out[c] = pr.accumulate ? out[c] + t : t;
+  }
+}
+
 // ---- grouped fp32 [M,N] -> bf16 copy + bf16 transpose (refresh of the trainable block weights after an update)
 struct RepackProblem {  // mirrors mfk.h
   const float* in; bf16* out_t; bf16* copy; int M, N;
@@ -585,9 +613,9 @@ extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
   else return MFK_ESHAPE;
 #undef LNB
   MFK_CHECK_LAUNCH();
-  if (part) {
+  if (part && !(accumulate & 2)) {  // bit 1: the caller reduces the partials later (mfk_partial_reduce_grouped)
     launch_pdl(partial_reduce_kernel, dim3((D + 31) / 32, 2), dim3(32, 32), 0, ST(stream), (const float*)part, grid, D,
-               2LL * D, (long long)D, dgamma, dbeta, accumulate);
+               2LL * D, (long long)D, dgamma, dbeta, accumulate & 1);
     MFK_CHECK_LAUNCH();
   }
   return MFK_OK;
@@ -740,6 +768,14 @@ extern "C" int mfk_repack_grouped(const void* problems_dev, int n_problems, int 
   if (!problems_dev || n_problems <= 0 || max_M <= 0 || max_N <= 0) return MFK_EARG;
   repack_grouped_kernel<<<dim3((max_N + 31) / 32, (max_M + 31) / 32, n_problems), dim3(32, 8), 0, ST(stream)>>>(
       static_cast<const RepackProblem*>(problems_dev));
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_partial_reduce_grouped(const void* problems_dev, int n_problems, int max_N, void* stream) {
+  if (!problems_dev || n_problems <= 0 || max_N <= 0) return MFK_EARG;
+  launch_pdl(partial_reduce_grouped_kernel, dim3((max_N + 31) / 32, 2, n_problems), dim3(32, 32), 0, ST(stream),
+             static_cast<const PartialReduceProblem*>(problems_dev));
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

@@ -42,6 +42,7 @@ class _Tower:
         self.N = self.T = self.M = 0
         self.ws: Dict[str, torch.Tensor] = {}
         self.gemm_ws: Optional[torch.Tensor] = None  # split-K workspace (vision tower only: one user stream)
+        self.ln_slot, self.ln_pending, self.ln_table, self.ln_key = 0, [], None, None  # deferred LN dgamma/dbeta
 
 
 class MapleEngine:
@@ -258,7 +259,8 @@ class MapleEngine:
             ws["dh"] = b("dh", (M, D), BF16)
             ws["dqkv"] = b("dqkv", (M, 3 * D), BF16)
             ws["delta"] = b("delta", (N * tw.heads * T,), F32)
-            ws["lnp"] = b("lnp", (2 * D * ops.ln_bwd_ctas(M),), F32)
+            # one dgamma/dbeta partial slot per LayerNorm backward of a step (2 per layer + final LN + ln_pre)
+            ws["lnp_all"] = b("lnp_all", (2 * L + 3, 2 * D * ops.ln_bwd_ctas(M)), F32)
             ws["csum"] = b("csum", (32 * 4 * D,), F32)
 
     # ------------------------------------------------------------------ prompt learner
@@ -350,6 +352,32 @@ class MapleEngine:
         """dW[Nout,Kin] = dy^T x straight from the row-major bf16 activations (MN-major UMMA operands)."""
         ops.gemm_at_b(dy16, x16, dW)
 
+    # ------------------------------------------------------------------ LayerNorm backward with deferred dgamma/dbeta
+    def _ln_bwd(self, tw: _Tower, dy, x, mean, rstd, gamma, *, g_in=None, g_out, g_out_bf16=None, dgamma=None,
+                dbeta=None, M=None):
+        """LayerNorm backward whose per-CTA dgamma/dbeta partials go to this call's own slot of the tower's partial
+        buffer; _ln_reduce() finishes every LayerNorm of the tower in one grouped launch (fixed order: the step's
+        launch sequence is static, so slot k is always the same LayerNorm)."""
+        if dgamma is None and dbeta is None:
+            ops.layernorm_bwd(dy, x, mean, rstd, gamma, g_in=g_in, g_out=g_out, g_out_bf16=g_out_bf16, M=M)
+            return
+        D = x.shape[-1]
+        rows = x.numel() // D if M is None else M
+        slot = tw.ln_slot
+        tw.ln_slot += 1
+        part = tw.ws["lnp_all"][slot]
+        ops.layernorm_bwd(dy, x, mean, rstd, gamma, g_in=g_in, g_out=g_out, g_out_bf16=g_out_bf16, dgamma=dgamma,
+                          dbeta=dbeta, partial_ws=part, M=M, defer=True)
+        tw.ln_pending.append((part, ops.ln_bwd_ctas(rows), D, dgamma, dbeta, False))
+
+    def _ln_reduce(self, tw: _Tower):
+        if tw.ln_pending:
+            key = (tw.ws["lnp_all"].data_ptr(), tw.M, len(tw.ln_pending))
+            if tw.ln_table is None or tw.ln_key != key:
+                tw.ln_table, tw.ln_key = ops.partial_reduce_table(tw.ln_pending, self.dev), key
+            ops.partial_reduce_grouped(tw.ln_table, tw.D)
+        tw.ln_pending, tw.ln_slot = [], 0
+
     def _last_block_bwd_rows(self, tw: _Tower, rows):
         """Backward of the last block's out-proj + MLP on the gathered rows. In: ws["g_r"] / ws["g16_r"] = gradient
         at the block output rows. Out: ws["g"] / ws["g16"] (full, zero except `rows`) = gradient after the attention
@@ -368,9 +396,9 @@ class MapleEngine:
             ops.gemm_at_b(ws["du_r"], ws["h2_r"], G[pre + "mlp.c_fc.weight"])
             ops.colsum(ws["du_r"], G[pre + "mlp.c_fc.bias"], ws["csum"])
         sr = ws["stat_r"]
-        ops.layernorm_bwd(ws["dh_r"], ws["x2_r"], sr[0], sr[1], w["ln_2.g"], g_in=g, g_out=g, g_out_bf16=g16,
+        self._ln_bwd(tw, ws["dh_r"], ws["x2_r"], sr[0], sr[1], w["ln_2.g"], g_in=g, g_out=g, g_out_bf16=g16,
                           dgamma=G[pre + "ln_2.weight"] if ln_grads else None,
-                          dbeta=G[pre + "ln_2.bias"] if ln_grads else None, partial_ws=ws["lnp"], M=g.shape[0])
+                          dbeta=G[pre + "ln_2.bias"] if ln_grads else None, M=g.shape[0])
         ops.gemm(g16, w["attn.out_proj.wT"], out_bf16=ws["dh_r"])
         if wg:
             ops.gemm_at_b(g16, ws["att_r"], G[pre + "attn.out_proj.weight"])
@@ -396,9 +424,9 @@ class MapleEngine:
             if wg:
                 self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)
                 ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
-            ops.layernorm_bwd(ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
+            self._ln_bwd(tw, ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
                               dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
-                              dbeta=G[pre + "ln_1.bias"] if ln_grads else None, partial_ws=ws["lnp"])
+                              dbeta=G[pre + "ln_1.bias"] if ln_grads else None)
             return
         # ---- MLP branch
         ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"], ws=tw.gemm_ws)
@@ -409,9 +437,9 @@ class MapleEngine:
         if wg:
             self._wgrad(tw, ws["du"], ws["h2"], G[pre + "mlp.c_fc.weight"], 4 * D, D)
             ops.colsum(ws["du"], G[pre + "mlp.c_fc.bias"], ws["csum"])
-        ops.layernorm_bwd(ws["dh"], ws["x2"][l], st[2], st[3], w["ln_2.g"], g_in=g, g_out=g, g_out_bf16=g16,
+        self._ln_bwd(tw, ws["dh"], ws["x2"][l], st[2], st[3], w["ln_2.g"], g_in=g, g_out=g, g_out_bf16=g16,
                           dgamma=G[pre + "ln_2.weight"] if ln_grads else None,
-                          dbeta=G[pre + "ln_2.bias"] if ln_grads else None, partial_ws=ws["lnp"])
+                          dbeta=G[pre + "ln_2.bias"] if ln_grads else None)
         # ---- attention branch
         da = ws["dh"]
         ops.gemm(g16, w["attn.out_proj.wT"], out_bf16=da, ws=tw.gemm_ws)
@@ -424,9 +452,9 @@ class MapleEngine:
         if wg:
             self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)
             ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
-        ops.layernorm_bwd(ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
+        self._ln_bwd(tw, ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
                           dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
-                          dbeta=G[pre + "ln_1.bias"] if ln_grads else None, partial_ws=ws["lnp"])
+                          dbeta=G[pre + "ln_1.bias"] if ln_grads else None)
 
     # ------------------------------------------------------------------ towers: embed + head rows
     def _vision_embed(self, img: torch.Tensor, train: bool):
@@ -535,9 +563,9 @@ class MapleEngine:
         ops.cast_bf16(dfeat, d16)
         dy = self._buf(tw.name + ".dy", (R, D), F32)
         ops.gemm(d16, proj, out_f32=dy)
-        ops.layernorm_bwd(dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=ws["g_r"], g_out_bf16=ws["g16_r"],
+        self._ln_bwd(tw, dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=ws["g_r"], g_out_bf16=ws["g16_r"],
                           dgamma=G[lnname + ".weight"] if ln_grads else None,
-                          dbeta=G[lnname + ".bias"] if ln_grads else None, partial_ws=ws["lnp"], M=R)
+                          dbeta=G[lnname + ".bias"] if ln_grads else None, M=R)
         self._last_block_bwd_rows(tw, rows)
         got = {}
         for l in reversed(range(tw.L)):
@@ -562,6 +590,8 @@ class MapleEngine:
         B, C, n, nd = img.shape[0], self.C, self.n, self.J - 1
         p, G = self.p, self.g
         self._text_cache_valid = False
+        for tw in (self.vis, self.txt):
+            tw.ln_slot, tw.ln_pending = 0, []
         # The two towers are independent until the logits head: the (small) text tower runs on a side stream so
         # its latency-bound kernels fill the gaps of the vision tower; inside a CUDA graph this becomes two
         # parallel branches.
@@ -584,13 +614,15 @@ class MapleEngine:
         with torch.cuda.stream(side):
             dt = self._tower_bwd(self.txt, dft, self.tproj, txs, tstat, self.txt_rows, "text_encoder.ln_final", C, 1)
             ops.prompt_splice_bwd(self.txt.ws["g"], None, self.d_ctx_t, C, self.Te, 1, n, False, False)
+            self._ln_reduce(self.txt)
         dv = self._tower_bwd(self.vis, dfi, self.vproj, vxs, vstat, self.cls_rows, "image_encoder.ln_post", B,
                              self.Tv - n)
         vws = self.vis.ws
-        ops.layernorm_bwd(vws["g"], self.vx0, self.vstat0[0], self.vstat0[1], p["image_encoder.ln_pre.weight"],
+        self._ln_bwd(self.vis, vws["g"], self.vx0, self.vstat0[0], self.vstat0[1], p["image_encoder.ln_pre.weight"],
                           g_out=vws["g"], dgamma=G["image_encoder.ln_pre.weight"] if ln_grads else None,
-                          dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None, partial_ws=vws["lnp"])
+                          dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None)
         ops.prompt_splice_bwd(vws["g"], None, self.d_shared, B, self.Tv, self.Tv - n, n, True, False)
+        self._ln_reduce(self.vis)
         main.wait_stream(side)
 
         # ---- prompt learner backward: dW, db and dx = dy W + d(prompt) for all projections in

@@ -87,12 +87,24 @@ def ln_bwd_ctas(M: int) -> int:
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, g_in=None, g_out, g_out_bf16=None, dgamma=None, dbeta=None,
-                  partial_ws=None, accumulate=False, M=None):
+                  partial_ws=None, accumulate=False, M=None, defer=False):
+    """defer: leave the per-CTA dgamma/dbeta partials in partial_ws (reduced later by partial_reduce_grouped)."""
     D = x.shape[-1]
     M = x.numel() // D if M is None else M
     call("mfk_layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma,
-         dbeta, partial_ws, int(accumulate), M, D, stream_ptr(),
-         kernels=1 + (dgamma is not None or dbeta is not None))
+         dbeta, partial_ws, int(accumulate) | (2 if defer else 0), M, D, stream_ptr(),
+         kernels=1 + ((dgamma is not None or dbeta is not None) and not defer))
+
+
+def partial_reduce_table(problems, device) -> torch.Tensor:
+    """Device table of mfk_partial_reduce_problem from (partial, P, N, out0, out1, accumulate) tuples."""
+    rows = [[pt.data_ptr(), P | (N << 32), o0.data_ptr() if o0 is not None else 0,
+             o1.data_ptr() if o1 is not None else 0, int(acc)] for pt, P, N, o0, o1, acc in problems]
+    return torch.tensor(rows, dtype=torch.int64, device=device).contiguous()
+
+
+def partial_reduce_grouped(table, max_N):
+    call("mfk_partial_reduce_grouped", table, table.shape[0], max_N, stream_ptr())
 
 
 def colsum(x, out, partial_ws, accumulate=False):

@@ -88,11 +88,17 @@ int mfk_layernorm_fwd(const float* x, const int* rowidx, const float* gamma, con
                       float* y_f32, float* x_save, float* mean, float* rstd, int M, int D, float eps,
                       void* stream);
 /* g_out = (g_in ? g_in : 0) + dLN(dy); optional bf16 copy; optional dgamma/dbeta (fixed-order two-stage
- * reduction; `accumulate` adds into them). partial_ws: 2*D*mfk_ln_bwd_ctas(M) floats. g_in may alias g_out. */
+ * reduction). partial_ws: 2*D*mfk_ln_bwd_ctas(M) floats. g_in may alias g_out. `accumulate`: bit 0 adds into
+ * dgamma/dbeta; bit 1 DEFERS the second stage — the per-CTA partials stay in partial_ws ([P][2][D], P =
+ * mfk_ln_bwd_ctas(M)) and the caller reduces many LayerNorms at once with mfk_partial_reduce_grouped.          */
 int mfk_ln_bwd_ctas(int M);
 int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
                       const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma,
                       float* dbeta, float* partial_ws, int accumulate, int M, int D, void* stream);
+typedef struct mfk_partial_reduce_problem {
+  const float* partial; int P, N; float* out0; float* out1; int accumulate, pad;   /* partial: [P][2][N] */
+} mfk_partial_reduce_problem;
+int mfk_partial_reduce_grouped(const void* problems_dev, int n_problems, int max_N, void* stream);
 /* out[N] (+)= column sums of x[M,N] (bias gradients). partial_ws: 32*N floats. */
 int mfk_colsum(const void* x, int is_bf16, long long ld, int M, int N, float* out, float* partial_ws,
                int accumulate, void* stream);
