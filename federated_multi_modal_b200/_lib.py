@@ -47,7 +47,7 @@ SIGNATURES = {
     "mfk_linear_small_bwd": [P, P, P, P, P, P, P, I, I, I, P],
     "mfk_linear_small_fwd_grouped": [P, I, I, P],
     "mfk_linear_small_bwd_grouped": [P, I, I, I, I, P],
-    "mfk_repack_grouped": [P, I, I, I, P],
+    "mfk_repack_grouped": [P, I, I, P],
     "mfk_partial_reduce_grouped": [P, I, I, P],
     "mfk_head_workspace_floats": [I, I, I],
     "mfk_head_forward_backward": [P, P, P, P, P, P, P, P, P, I, I, I, P],

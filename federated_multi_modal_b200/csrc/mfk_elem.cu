@@ -84,26 +84,28 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
               const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* g_in,
               float* g_out, bf16* __restrict__ g16, float* __restrict__ partial, int M) {
   constexpr int D = 128 * VEC;
-  __shared__ __align__(16) float red[kLnWarps][D];
+  // per-warp dgamma / dbeta accumulators live in shared memory (lane-private entries, no synchronisation inside the
+  // row loop): the 48 registers they used to take now hold the prefetched residual gradient, so one row costs ONE
+  // memory round trip (x, dy, g_in issued together) instead of two.
+  __shared__ __align__(16) float acc[kLnWarps][2][D];
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float4 dg[VEC], db[VEC];
+  float4* mydg = reinterpret_cast<float4*>(&acc[warp][0][0]);
+  float4* mydb = reinterpret_cast<float4*>(&acc[warp][1][0]);
+  if (partial) {
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 gam[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    for (int i = 0; i < VEC; ++i) mydg[lane + 32 * i] = mydb[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4* gam4 = reinterpret_cast<const float4*>(gamma);
 
   for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
-    const float mean = mean_i[row], rstd = rstd_i[row];
-    float4 xh[VEC], d[VEC];
-    float s1 = 0.f, s2 = 0.f;
+    float4 xh[VEC], d[VEC], r[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const int c4 = lane + 32 * i;
-      float4 xv = reinterpret_cast<const float4*>(x + (size_t)row * D)[c4];
+      xh[i] = reinterpret_cast<const float4*>(x + (size_t)row * D)[c4];
       if (DY_BF16) {
         uint2 u = reinterpret_cast<const uint2*>(static_cast<const bf16*>(dy_) + (size_t)row * D)[c4];
         float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
@@ -111,10 +113,24 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
       } else {
         d[i] = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + (size_t)row * D)[c4];
       }
-      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-      dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y; dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
-      db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
-      d[i].x *= gam[i].x; d[i].y *= gam[i].y; d[i].z *= gam[i].z; d[i].w *= gam[i].w;
+      r[i] = g_in ? reinterpret_cast<const float4*>(g_in + (size_t)row * D)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float mean = mean_i[row], rstd = rstd_i[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c4 = lane + 32 * i;
+      xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd,
+                          (xh[i].w - mean) * rstd);
+      if (partial) {
+        float4 a = mydg[c4], b = mydb[c4];
+        a.x += d[i].x * xh[i].x; a.y += d[i].y * xh[i].y; a.z += d[i].z * xh[i].z; a.w += d[i].w * xh[i].w;
+        b.x += d[i].x; b.y += d[i].y; b.z += d[i].z; b.w += d[i].w;
+        mydg[c4] = a;
+        mydb[c4] = b;
+      }
+      const float4 gm = __ldg(gam4 + c4);
+      d[i].x *= gm.x; d[i].y *= gm.y; d[i].z *= gm.z; d[i].w *= gm.w;
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
     }
@@ -128,29 +144,21 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
       o.y = (d[i].y - s1 - xh[i].y * s2) * rstd;
       o.z = (d[i].z - s1 - xh[i].z * s2) * rstd;
       o.w = (d[i].w - s1 - xh[i].w * s2) * rstd;
-      if (g_in) {
-        float4 r = reinterpret_cast<const float4*>(g_in + (size_t)row * D)[c4];
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      if (g_in) { o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w; }
       reinterpret_cast<float4*>(g_out + (size_t)row * D)[c4] = o;
       if (g16) reinterpret_cast<uint2*>(g16 + (size_t)row * D)[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     }
   }
   if (!partial) return;
-  // cross-warp reduction of the per-lane column partials (fixed order over warps)
+  // cross-warp reduction of the per-warp column sums (fixed order over warps)
+  __syncthreads();
   float* pg = partial + (size_t)blockIdx.x * 2 * D;
-  for (int half = 0; half < 2; ++half) {
-    __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += kLnWarps * 32) {
+    const int half = c / D, col = c % D;
+    float a = 0.f;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i)
-      reinterpret_cast<float4*>(&red[warp][0])[lane + 32 * i] = half == 0 ? dg[i] : db[i];
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += kLnWarps * 32) {
-      float a = 0.f;
-#pragma unroll
-      for (int w = 0; w < kLnWarps; ++w) a += red[w][c];
-      pg[half * D + c] = a;
-    }
+    for (int w = 0; w < kLnWarps; ++w) a += acc[w][half][col];
+    pg[c] = a;
   }
 }
 
@@ -546,12 +554,17 @@ __global__ void partial_reduce_grouped_kernel(const PartialReduceProblem* __rest
 // ---- grouped fp32 [M,N] -> bf16 copy + bf16 transpose (refresh of the trainable block weights after an update)
 struct RepackProblem {  // mirrors mfk.h
   const float* in; bf16* out_t; bf16* copy; int M, N;
+  int tile0, tiles_n;  // first global 32x32 tile index of this problem; its tiles per row
 };
-__global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab) {
+// grid.x = total number of 32x32 tiles over all problems: every block finds its problem by a short scan
+__global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab, int n_problems) {
   __shared__ float tile[32][33];
-  const RepackProblem pr = tab[blockIdx.z];
-  const int n0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-  if (n0 >= pr.N || m0 >= pr.M) return;  // uniform per block
+  int pi = 0;
+  while (pi + 1 < n_problems && (int)blockIdx.x >= tab[pi + 1].tile0) ++pi;
+  const RepackProblem pr = tab[pi];
+  const int t = (int)blockIdx.x - pr.tile0;
+  const int n0 = (t % pr.tiles_n) * 32, m0 = (t / pr.tiles_n) * 32;
+  if (m0 >= pr.M) return;  // uniform per block
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int m = m0 + i, n = n0 + threadIdx.x;
     float v = 0.f;
@@ -764,10 +777,10 @@ extern "C" int mfk_linear_small_bwd_grouped(const void* problems_dev, int n_prob
   return MFK_OK;
 }
 
-extern "C" int mfk_repack_grouped(const void* problems_dev, int n_problems, int max_M, int max_N, void* stream) {
-  if (!problems_dev || n_problems <= 0 || max_M <= 0 || max_N <= 0) return MFK_EARG;
-  repack_grouped_kernel<<<dim3((max_N + 31) / 32, (max_M + 31) / 32, n_problems), dim3(32, 8), 0, ST(stream)>>>(
-      static_cast<const RepackProblem*>(problems_dev));
+extern "C" int mfk_repack_grouped(const void* problems_dev, int n_problems, int total_tiles, void* stream) {
+  if (!problems_dev || n_problems <= 0 || total_tiles <= 0) return MFK_EARG;
+  repack_grouped_kernel<<<total_tiles, dim3(32, 8), 0, ST(stream)>>>(static_cast<const RepackProblem*>(problems_dev),
+                                                                      n_problems);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

@@ -197,9 +197,8 @@ class MapleEngine:
             probs = [(w[lin + ".master"], w[lin + ".wT"], w[lin + ".w"]) for tw in (self.vis, self.txt) for w in tw.w
                      for lin in _LIN if lin + ".master" in w]
             self._repack_table = ops.repack_table(probs, self.dev) if probs else False
-            self._repack_max = (max(m.shape[0] for m, _, _ in probs), max(m.shape[1] for m, _, _ in probs)) if probs else (0, 0)
         if self._repack_table is not False:
-            ops.repack_grouped(self._repack_table, *self._repack_max)
+            ops.repack_grouped(*self._repack_table)
         self._text_cache_valid = False
 
     # ------------------------------------------------------------------ workspaces

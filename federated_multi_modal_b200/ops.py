@@ -187,14 +187,20 @@ def linear_small_bwd_grouped(table, max_m, max_N, max_K):
     call("mfk_linear_small_bwd_grouped", table, table.shape[0], max_m, max_N, max_K, stream_ptr(), kernels=2)
 
 
-def repack_table(problems, device) -> torch.Tensor:
-    """Device table of mfk_repack_problem from (master fp32 [M,N], out_t bf16 [N,M], copy bf16 [M,N]) triples."""
-    rows = [[w.data_ptr(), t.data_ptr(), c.data_ptr(), w.shape[0] | (w.shape[1] << 32)] for w, t, c in problems]
-    return torch.tensor(rows, dtype=torch.int64, device=device).contiguous()
+def repack_table(problems, device):
+    """(device table of mfk_repack_problem, total 32x32 tiles) from (master fp32 [M,N], out_t bf16 [N,M],
+    copy bf16 [M,N]) triples."""
+    rows, tile0 = [], 0
+    for w, t, c in problems:
+        M, N = w.shape
+        tm, tn = (M + 31) // 32, (N + 31) // 32
+        rows.append([w.data_ptr(), t.data_ptr(), c.data_ptr(), M | (N << 32), tile0 | (tn << 32)])
+        tile0 += tm * tn
+    return torch.tensor(rows, dtype=torch.int64, device=device).contiguous(), tile0
 
 
-def repack_grouped(table, max_M, max_N):
-    call("mfk_repack_grouped", table, table.shape[0], max_M, max_N, stream_ptr())
+def repack_grouped(table, total_tiles):
+    call("mfk_repack_grouped", table, table.shape[0], total_tiles, stream_ptr())
 
 
 def head_workspace_floats(B, C, E) -> int:

@@ -157,8 +157,9 @@ int mfk_linear_small_bwd_grouped(const void* problems_dev, int n_problems, int m
  * copy[M,N] = bf16(in), out_t[N,M] = bf16(in)^T (the K-major operand of the dgrad GEMM).               */
 typedef struct mfk_repack_problem {
   const float* in; void* out_t; void* copy; int M, N;
+  int tile0, tiles_n;   /* first global 32x32 tile of this problem (ascending), ceil(N/32) */
 } mfk_repack_problem;
-int mfk_repack_grouped(const void* problems_dev, int n_problems, int max_M, int max_N, void* stream);
+int mfk_repack_grouped(const void* problems_dev, int n_problems, int total_tiles, void* stream);
 
 /* ------------------------------------------------------------------ logits + loss head (trainers/maple.py:325-372)
  * label == NULL: inference, only `logits` [B,C] is written. Otherwise also loss[1], d_img[B,E], d_txt[C,E].

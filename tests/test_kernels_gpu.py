@@ -327,7 +327,7 @@ def test_grouped_small_linear_and_repack_match_single_calls():
     ws = [rnd(96, 160, seed=70), rnd(512, 2048, seed=71)]
     trip = [(w, torch.empty(w.shape[1], w.shape[0], device=DEV, dtype=BF16),
              torch.empty(w.shape, device=DEV, dtype=BF16)) for w in ws]
-    ops.repack_grouped(ops.repack_table(trip, DEV), 512, 2048)
+    ops.repack_grouped(*ops.repack_table(trip, DEV))
     for w, t, c in trip:
         assert torch.equal(c, w.to(BF16)) and torch.equal(t, w.to(BF16).t().contiguous())
 
