@@ -120,7 +120,8 @@ struct EpiCtx {
 // row0 = first row of the 32-row group, col = first column, ok = this lane's element range is inside [M, N).
 template <int EPI>
 __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], const float4 (&rv)[EPI == 3 ? 8 : 1],
-                                             const uint4 (&av)[EPI == 2 ? 4 : 1], int row0, int col, bool ok) {
+                                             const uint4 (&av)[EPI == 2 ? 4 : 1], int row0, int col, bool ok,
+                                             uint32_t pp) {
   if (EPI != 2 && c.p.bias && col < c.p.N) {
     const float4* b4 = reinterpret_cast<const float4*>(c.p.bias + col);
 #pragma unroll
@@ -129,9 +130,18 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
       v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
     }
   }
-  // previous TMA stores of this warp must have finished READING the staging buffer
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  // A single bf16 output needs only half of the 4 KB staging buffer per chunk: the two halves are used in turn
+  // (pp = chunk parity) and only the store before the previous one must have finished READING its half, so the TMA
+  // store of chunk i overlaps the arithmetic of chunk i + 1. Otherwise the whole buffer is reused every chunk.
+  const GemmParams& p = c.p;
+  const bool trc = (threadIdx.x == 128);  // warp 4 lane 0
+  if (trc) GTRACE(2, 56);
+  const bool pingpong = EPI != 1 && EPI != 3 && c.p.out16 && !c.p.out32;
+  const uint32_t poff = pingpong ? (pp & 1u) * 2048u : 0u;
+  if (pingpong) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
+  if (trc) GTRACE(2, 57);
   if (EPI == 1) {
     if (c.has_pre) {
 #pragma unroll
@@ -166,15 +176,17 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
     if (c.p.out16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.row64a + ((j ^ c.x64) << 4)),
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.row64a + poff + ((j ^ c.x64) << 4)),
                      "r"(pack_bf16(v[8 * j], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
                      "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
                      : "memory");
     }
+    if (trc) GTRACE(2, 58);
     fence_proxy_async();
     __syncwarp();
+    if (trc) GTRACE(2, 59);
     if (c.lane == 0) {
-      if (c.p.out16) tma_store_2d(c.tmO16, c.sbuf, col, row0);
+      if (c.p.out16) tma_store_2d(c.tmO16, c.sbuf + poff, col, row0);
       if (c.has_pre) tma_store_2d(c.tmPre, c.sbuf + 2048, col, row0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
@@ -203,7 +215,7 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
 // kSplitK instantiations of the kernel contain it (its registers would weigh on the plain epilogue loop otherwise).
 template <int EPI>
 __device__ __forceinline__ void splitk_unit(const EpiCtx& c, uint32_t taddr, int w, int half, int q, int ew, int m0,
-                                         int n0, int rem_idx, int slice, uint64_t* tempty) {
+                                         int n0, int rem_idx, int slice, uint64_t* tempty, uint32_t& pp) {
   const GemmParams& p = c.p;
   const int lane = c.lane;
     // partial layout: [unit][row group rq 0..3][chunk cc 0..7][j 0..7][lane] float4 — one warp store/load
@@ -313,7 +325,7 @@ __device__ __forceinline__ void splitk_unit(const EpiCtx& c, uint32_t taddr, int
 #pragma unroll
           for (int j = 0; j < 4; ++j) av[j] = __ldg(a4 + j);
         }
-        finish_chunk<EPI>(c, v, rv, av, m0 + rq * 32, col, ok);
+        finish_chunk<EPI>(c, v, rv, av, m0 + rq * 32, col, ok, pp++);
       }
       if (ew == 0 && lane == 0) GTRACE(2, 45);
       if (wpp > 1 && j0 + kEpiWarps / wpp < npieces)  // buffers are reused by the next round
@@ -541,6 +553,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     };
     if (n_mine > 0) fetch_ops(tile_of(0), half * 32);
+    uint32_t nchunk = 0;  // chunks finished by this warp (ping-pong parity of the staging buffer)
     for (int it = 0; it < n_mine; ++it) {
       const int t = tile_of(it);
       int m0, n0, w;
@@ -557,7 +570,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         if (warp == 4 && lane == 0) GTRACE(2, 2 * it);
-        splitk_unit<EPI>(ctx, taddr, w, half, q, warp - 4, m0, n0, rem_idx, slice, &tempty_bar[acc]);
+        splitk_unit<EPI>(ctx, taddr, w, half, q, warp - 4, m0, n0, rem_idx, slice, &tempty_bar[acc], nchunk);
         if (EPI >= 2 && it + 1 < n_mine) fetch_ops(tile_of(it + 1), half * 32);
         continue;
       }
@@ -585,13 +598,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           waited = true;
           if (warp == 4 && lane == 0) GTRACE(2, 2 * it);
         }
+        if (it == 1 && warp == 4 && lane == 0) GTRACE(2, 48 + 3 * (c >> 6));
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tc_wait_ld();
+        if (it == 1 && warp == 4 && lane == 0) GTRACE(2, 49 + 3 * (c >> 6));
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        finish_chunk<EPI>(ctx, v, rv, av, m0 + q * 32, col, ok);
+        finish_chunk<EPI>(ctx, v, rv, av, m0 + q * 32, col, ok, nchunk++);
+        if (it == 1 && warp == 4 && lane == 0) GTRACE(2, 50 + 3 * (c >> 6));
       }
       if (!waited) {  // narrow tile: this warp had no chunk, but it still takes part in the hand-shake
         mbar_wait(&tfull_bar[acc], acc_phase);

@@ -60,6 +60,11 @@ for name, m, n, k, epi in SHAPES:
         if int(ep[40]) > 0:
             line.append("  split-K unit: partial written @%d | fenced+barrier @%d | all slices seen @%d | slices summed @%d | "
                         "combined @%d | finished @%d" % tuple(rel(ep[i]) for i in range(40, 46)))
+        if int(ep[48]) > 0:
+            line.append("  tile1 chunks (start / tmem ready / chunk done): " + " | ".join(
+                "%d/%d/%d" % tuple(rel(ep[48 + 3 * k + j]) for j in range(3)) for k in range(4) if int(ep[48 + 3 * k]) > 0))
+        if int(ep[56]) > 0:
+            line.append("  last chunk: enter finish %d | bias+store-wait done %d | staged %d | fenced %d" % tuple(rel(ep[i]) for i in range(56, 60)))
         line.append(f"  stores drained @{rel(ep[62])}")
         print("\n".join(line))
     # whole-grid summary in cycles
