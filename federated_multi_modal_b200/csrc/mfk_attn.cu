@@ -444,7 +444,12 @@ struct AttnTcParams {
   float* lse;
   int T, Tk, heads, m_tiles, total_items;
   float c1;  // softmax scale * log2(e)
+  long long* trace;  // optional debug: clock64 stamps of CTA 0, softmax warp 0 (tools/attn_trace.py fwd); NULL in production
 };
+#define FTRC()                                                                                  \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && warp == 0 && lane == 0 && ftrc_n < 60) p.trace[ftrc_n++] = clock64(); \
+  } while (0)
 
 // Work unit = one (sequence, head): K and V are loaded once and shared by its (<= 2) 128-query tiles, whose S/O
 // accumulators use the two 256-column TMEM buffers. Q+K of the next unit are fetched as soon as this unit's QK^T
@@ -458,35 +463,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int Tk = p.Tk, D = p.heads * HD, NT = p.m_tiles;
   const uint32_t kvBytes = (uint32_t)Tk * 128u, qBytes = (uint32_t)NT * 16384u;
   const int nkb = (Tk + 63) / 64;  // 64-key column blocks of P
+  const uint32_t pBytes = (uint32_t)nkb * 16384u;
   uint8_t* sQ = smem;                       // [NT x 128 rows x 128 B]
   uint8_t* sK = sQ + qBytes;                // [Tk x 128 B]
-  uint8_t* sV = sK + kvBytes;               // [2][Tk x 128 B]
-  uint8_t* sP = sV + 2 * kvBytes;           // [nkb][128 x 128 B]
-  float* sx = reinterpret_cast<float*>(sP + (size_t)nkb * 16384);  // [2 halves][128 rows] max / sum exchange
+  uint8_t* sV = sK + kvBytes;               // [Tk x 128 B]
+  uint8_t* sP = sV + kvBytes;               // [2][nkb][128 x 128 B]: P of tile g in buffer g & 1 (also stages O)
+  float* sx = reinterpret_cast<float*>(sP + 2 * (size_t)pBytes);  // [2 halves][128 rows] max / sum exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 256);
   uint64_t* qk_full = bars;         // [1]
-  uint64_t* v_full = bars + 1;      // [2]
-  uint64_t* s_full = bars + 3;      // [2] per query tile
+  uint64_t* v_full = bars + 1;      // [1]
+  uint64_t* s_full = bars + 3;      // [2] per accumulator buffer (tile parity)
   uint64_t* o_full = bars + 5;      // [2]
   uint64_t* tmem_free = bars + 7;   // [2]
-  uint64_t* p_full = bars + 9;      // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* p_full = bars + 9;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Tiles are numbered g = unit * NT + query tile over the whole CTA; tile g uses accumulator / P buffer g & 1 and the
+  // barrier phase (g >> 1) & 1, so consecutive tiles always alternate buffers (also when NT == 1).
+  const int n_tiles = n_units * NT;
 
   if (warp == TC_SOFTMAX_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
       mbar_init(qk_full, 1);
+      mbar_init(v_full, 1);
       for (int b = 0; b < 2; ++b) {
-        mbar_init(&v_full[b], 1);
         mbar_init(&s_full[b], 1);
         mbar_init(&o_full[b], 1);
         mbar_init(&tmem_free[b], TC_SOFTMAX_WARPS);
+        mbar_init(&p_full[b], TC_SOFTMAX_WARPS);
       }
-      mbar_init(p_full, TC_SOFTMAX_WARPS);
       fence_barrier_init();
     }
     __syncwarp();
@@ -509,69 +518,138 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == TC_SOFTMAX_WARPS) {
     // ============================ control: TMA loads + MMA issue (one thread) ============================
     if (lane == 0) {
-      auto issue_loads = [&](int u) {
+      auto issue_qk = [&](int u) {
         int n, h;
         unit_coords(u, n, h);
         mbar_arrive_expect_tx(qk_full, qBytes + kvBytes);
         tma_load_2d(&tmQ, qk_full, sQ, h * HD, n * p.T);
         tma_load_2d(&tmKV, qk_full, sK, D + h * HD, n * p.T);
-        mbar_arrive_expect_tx(&v_full[u & 1], kvBytes);
-        tma_load_2d(&tmKV, &v_full[u & 1], sV + (u & 1) * kvBytes, 2 * D + h * HD, n * p.T);
+      };
+      auto issue_v = [&](int u) {
+        int n, h;
+        unit_coords(u, n, h);
+        mbar_arrive_expect_tx(v_full, kvBytes);
+        tma_load_2d(&tmKV, v_full, sV, 2 * D + h * HD, n * p.T);
       };
       const uint32_t idesc_s = umma_idesc_bf16(128, Tk, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       const int ksteps = Tk / 16;
-      if (n_units > 0) issue_loads(0);
-      uint32_t pctr = 0;
-      for (int u = 0; u < n_units; ++u) {
-        const uint32_t par = (uint32_t)u & 1u;
-        mbar_wait(qk_full, par);
-        for (int mt = 0; mt < NT; ++mt) {
-          mbar_wait(&tmem_free[mt], par ^ 1u);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ) + (uint32_t)mt * 16384u);
-          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK));
+      // Event order seen by this thread (softmax warps: pass(g) -> p_full(g) -> epilogue(g - 1) frees the accumulator
+      // that tile g + 1 will use): PV(g) on p_full(g), then S(g + 1) on tmem_free; Q / K of the next unit are fetched
+      // as soon as the unit's last S has retired, V once its last P V has.
+      auto issue_s = [&](int t) {
+        const int u = t / NT, mt = t % NT, b = t & 1;
+        if (mt == 0) mbar_wait(qk_full, (uint32_t)u & 1u);
+        mbar_wait(&tmem_free[b], (((uint32_t)t >> 1) & 1u) ^ 1u);  // epilogue of tile t - 2 drained this buffer
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ) + (uint32_t)mt * 16384u);
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + (uint32_t)mt * 256u, adesc + 2ull * k, bdesc + 2ull * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[mt]);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc + 2ull * k, bdesc + 2ull * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+        if (mt == NT - 1 && u + 1 < n_units) {  // every MMA that reads Q / K of unit u has been issued: refill
+          mbar_wait(&s_full[b], ((uint32_t)t >> 1) & 1u);
+          issue_qk(u + 1);
         }
-        // all MMAs issued so far (incl. the previous unit's P V) have retired once s_full[NT-1] completes:
-        // Q, K and the other V buffer can be refilled for the next unit
-        mbar_wait(&s_full[NT - 1], par);
-        if (u + 1 < n_units) issue_loads(u + 1);
-        mbar_wait(&v_full[u & 1], (uint32_t)(u >> 1) & 1u);
-        const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV + (u & 1) * kvBytes);
-        for (int mt = 0; mt < NT; ++mt, ++pctr) {
-          mbar_wait(p_full, pctr & 1u);
-          tc_fence_after();
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adesc = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
-            const uint64_t bdesc = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
-            umma_bf16(tmem_base + (uint32_t)mt * 256u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
-          }
-          umma_commit(&o_full[mt]);
+      };
+      if (n_units > 0) {
+        issue_qk(0);
+        issue_v(0);
+        issue_s(0);
+      }
+      const uint32_t vbase = smem_u32(sV);
+      for (int g = 0; g < n_tiles; ++g) {
+        const int u = g / NT, mt = g % NT, b = g & 1;
+        // S of the NEXT tile first: its accumulator is freed by epilogue(g - 1), which the softmax warps run right
+        // after handing P(g) over, so S(g + 1) is complete by the time they come back for it; PV(g) is not needed
+        // before epilogue(g), a whole softmax later.
+        if (g + 1 < n_tiles) issue_s(g + 1);
+        if (mt == 0 && u > 0) {  // V is single-buffered: the previous unit's last P V must have retired
+          mbar_wait(&o_full[(g - 1) & 1], ((uint32_t)(g - 1) >> 1) & 1u);
+          issue_v(u);
         }
+        mbar_wait(&p_full[b], ((uint32_t)g >> 1) & 1u);
+        if (mt == 0) mbar_wait(v_full, (uint32_t)u & 1u);
+        tc_fence_after();
+        const uint32_t pbase = smem_u32(sP) + (uint32_t)b * pBytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t adesc = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+          const uint64_t bdesc = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
+          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[b]);
       }
     }
     __syncwarp();
   } else {
     // ============================ softmax + epilogue warps ============================
+    // Software pipeline over tiles: softmax(g) -> P(g) handed to the tensor core -> epilogue(g - 1). The P V MMAs
+    // of tile g run under the epilogue of tile g - 1 and the softmax of tile g + 1 instead of being waited for.
     const int q = warp & 3, half = warp >> 2;
     const int rl = q * 32 + lane;  // row inside the 128-row tile == TMEM lane
-    const uint32_t prow = smem_u32(sP) + (uint32_t)rl * 128u;
     const uint32_t x7 = (uint32_t)rl & 7u;
-    for (int u = 0; u < n_units; ++u) {
+    int ftrc_n = 0;
+    // state of the tile whose epilogue is still pending
+    float l_prev = 0.f, mc_prev = 0.f;
+    auto epilogue = [&](int g, float l, float mc) {
+      const int u = g / NT, mt = g % NT, b = g & 1;
       int n, h;
       unit_coords(u, n, h);
-      const uint32_t par = (uint32_t)u & 1u;
-      for (int mt = 0; mt < NT; ++mt) {
-      const int b = mt;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * 256u;
+      mbar_wait(&o_full[b], ((uint32_t)g >> 1) & 1u);
+      tc_fence_after();
+      FTRC();  // O = P V ready
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      // O tile -> bf16 staged in this tile's (now idle) P buffer -> coalesced 128-byte row stores
+      const uint32_t obase = smem_u32(sP) + (uint32_t)b * pBytes;
+      {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(half * 32), r);
+        tc_wait_ld();
+        const uint32_t orow = obase + (uint32_t)rl * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(orow + ((((uint32_t)half * 4 + j) ^ x7) << 4)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv))
+                       : "memory");
+      }
+      const int row = mt * 128 + rl;
+      if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[b]);
+      asm volatile("bar.sync 5, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int idx = (int)threadIdx.x + m * (TC_SOFTMAX_WARPS * 32);
+        const int r_ = idx >> 3, ch = idx & 7;
+        if (mt * 128 + r_ < p.T) {
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(obase + (uint32_t)r_ * 128u + (((uint32_t)ch ^ ((uint32_t)r_ & 7u)) << 4)));
+          *reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T + mt * 128 + r_) * D + h * HD + ch * 8) = v;
+        }
+      }
+      // the buffer is overwritten by the P of tile g + 2: every thread must have read its part of the staged O
+      asm volatile("bar.sync 5, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
+      FTRC();  // epilogue done
+    };
+    for (int g = 0; g < n_tiles; ++g) {
+      const int mt = g % NT, b = g & 1;
+      const uint32_t par = ((uint32_t)g >> 1) & 1u;
+      const uint32_t prow = smem_u32(sP) + (uint32_t)b * pBytes + (uint32_t)rl * 128u;
       const int row = mt * 128 + rl;  // query index inside the sequence
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * 256u;
       const int kmax = CAUSAL ? min(p.T, row + 1) : p.T;  // keys [0, kmax) are visible
+      FTRC();  // about to wait for S
       mbar_wait(&s_full[b], par);
       tc_fence_after();
+      FTRC();  // S ready
       float mx = -INFINITY;
       for (int c = half * 32; c < Tk; c += 64) {
         uint32_t r[32];
@@ -590,6 +668,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       sx[half * 128 + rl] = mx;
       pair_sync(q);
+      FTRC();  // pass 1 (row max) done
       mx = fmaxf(mx, sx[(half ^ 1) * 128 + rl]);
       const float mc = (mx == -INFINITY) ? 0.f : mx * p.c1;
       float l = 0.f;
@@ -624,38 +703,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      FTRC();  // pass 2 (exp, P staged) done
       pair_sync(q);
       l += sx[(half ^ 1) * 128 + rl];
-      // ---- epilogue: O = (P V) / l ; each warp of the pair writes 32 of the 64 head-dim columns
-      mbar_wait(&o_full[b], par);
-      tc_fence_after();
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      bf16* orow = p.out + ((size_t)n * p.T + row) * D + h * HD;
-      {
-        const int c = half * 32;
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
-        tc_wait_ld();
-        if (row < p.T) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-            v.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-            v.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-            v.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + c + 8 * j) = v;
-          }
-        }
-      }
-      if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_free[b]);
-      pair_sync(q);  // the partner has consumed this warp's partial sum before the next item overwrites it
-      }
+      pair_sync(q);  // the partner has consumed this warp's partial sum before the next tile overwrites it
+      if (g > 0) epilogue(g - 1, l_prev, mc_prev);
+      l_prev = l;
+      mc_prev = mc;
     }
+    if (n_tiles > 0) epilogue(n_tiles - 1, l_prev, mc_prev);
   }
   tc_fence_before();
   __syncthreads();
@@ -667,6 +724,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 int g_attn_sms = 0;
 }  // namespace
+static long long* g_attn_trace = nullptr;
 
 extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int heads, int causal,
                                void* stream) {
@@ -688,6 +746,7 @@ extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, in
   p.m_tiles = (T + 127) / 128;
   p.total_items = N * heads;  // work units = (sequence, head)
   p.c1 = 0.125f * kLog2e;
+  p.trace = g_attn_trace;
   CUtensorMap tmQ, tmKV;
   int rc = mfk_make_tmap_2d(&tmQ, qkv, 2, (uint64_t)N * T, (uint64_t)3 * D, (uint64_t)3 * D,
                             (uint32_t)(128 * p.m_tiles), 64, 128);
@@ -696,7 +755,7 @@ extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, in
                              128)) != MFK_OK)
     return rc;
   const int nkb = (p.Tk + 63) / 64;
-  const size_t smem = (size_t)p.m_tiles * 16384 + 3 * (size_t)p.Tk * 128 + (size_t)nkb * 16384 + 1024 + 128 + 1024;
+  const size_t smem = (size_t)p.m_tiles * 16384 + 2 * (size_t)p.Tk * 128 + 2 * (size_t)nkb * 16384 + 1024 + 128 + 1024;
   const int grid = p.total_items < g_attn_sms ? p.total_items : g_attn_sms;
   cudaError_t e;
   if (causal) {
@@ -1366,7 +1425,6 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
 }
 }  // namespace
 
-static long long* g_attn_trace = nullptr;
 // debug hook: device buffer of 2*64 int64 receiving clock64 stamps of CTA 0 (NULL disables)
 extern "C" int mfk_debug_set_attn_trace(void* dev_buf) {
   g_attn_trace = static_cast<long long*>(dev_buf);
