@@ -43,6 +43,9 @@ SIGNATURES = {
     "mfk_transpose_bf16": [P, I, L, P, L, P, L, I, I, P],
     "mfk_cast_f32_bf16": [P, P, L, P],
     "mfk_split_bf16x3": [P, P, I, I, P],
+    "mfk_quickgelu_split_bf16x3": [P, P, I, I, P],
+    "mfk_patch_im2col_f32": [P, P, I, I, P],
+    "mfk_attn_fwd_f32": [P, P, I, I, I, I, P],
     "mfk_linear_small_fwd": [P, P, P, P, I, I, I, P],
     "mfk_linear_small_bwd": [P, P, P, P, P, P, P, I, I, I, P],
     "mfk_linear_small_fwd_grouped": [P, I, I, P],

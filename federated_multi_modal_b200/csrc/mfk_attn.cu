@@ -1465,3 +1465,90 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   if (e != cudaSuccess) return (int)e;
   return MFK_OK;
 }
+
+// =====================================================================================================
+// fp32 reference-precision attention forward (the "fp32 mode" of the parity contract: logits within 1e-3 of the
+// reference's fp32 path). Plain SIMT: one CTA per (sequence, head, 32-query block), K and V of the head in shared
+// memory as fp32, one warp per query row at a time (lanes over keys for the scores, lanes over the 64 head dims for
+// P V). Throughput is irrelevant here; every product and sum is fp32.
+namespace {
+constexpr int F32_QBLK = 32, F32_WARPS = 8;
+template <bool CAUSAL>
+__global__ void __launch_bounds__(F32_WARPS * 32)
+attn_fwd_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int heads) {
+  extern __shared__ float sm_f32[];
+  const int D = heads * HD;
+  float* sK = sm_f32;                     // [T][65] (padded: conflict-free column reads)
+  float* sV = sK + (size_t)T * 65;        // [T][64]
+  float* sP = sV + (size_t)T * 64;        // [F32_WARPS][T] probabilities of the row a warp is working on
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * F32_QBLK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = qkv + (size_t)n * T * 3 * D + h * HD;
+  const int kend = CAUSAL ? min(T, q0 + F32_QBLK) : T;  // keys any row of this block can see
+  for (int i = threadIdx.x; i < kend * HD; i += blockDim.x) {
+    const int r = i / HD, c = i % HD;
+    sK[r * 65 + c] = base[(size_t)r * 3 * D + D + c];
+    sV[r * 64 + c] = base[(size_t)r * 3 * D + 2 * D + c];
+  }
+  __syncthreads();
+  float* myP = sP + (size_t)warp * T;
+  for (int qi = q0 + warp; qi < min(T, q0 + F32_QBLK); qi += F32_WARPS) {
+    const float* qrow = base + (size_t)qi * 3 * D;
+    const float q_lo = qrow[lane], q_hi = qrow[lane + 32];
+    const int kmax = CAUSAL ? qi + 1 : T;
+    float mx = -INFINITY;
+    for (int k0 = 0; k0 < kmax; k0 += 32) {
+      const int k = k0 + lane;
+      const int kk = min(k, kmax - 1);  // clamped: every lane runs the same shuffles, the result is masked below
+      float a = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < 32; ++c) {
+        a = fmaf(__shfl_sync(0xffffffffu, q_lo, c), sK[kk * 65 + c], a);
+        a = fmaf(__shfl_sync(0xffffffffu, q_hi, c), sK[kk * 65 + 32 + c], a);
+      }
+      const float sc = k < kmax ? a * 0.125f : -INFINITY;
+      if (k < kmax) myP[k] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    float l = 0.f;
+    for (int k = lane; k < kmax; k += 32) {
+      const float e = expf(myP[k] - mx);
+      myP[k] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    __syncwarp();
+    float o_lo = 0.f, o_hi = 0.f;
+    for (int k = 0; k < kmax; ++k) {
+      const float pk = myP[k];
+      o_lo = fmaf(pk, sV[k * 64 + lane], o_lo);
+      o_hi = fmaf(pk, sV[k * 64 + 32 + lane], o_hi);
+    }
+    const float inv = 1.f / l;
+    float* orow = out + ((size_t)n * T + qi) * D + h * HD;
+    orow[lane] = o_lo * inv;
+    orow[lane + 32] = o_hi * inv;
+    __syncwarp();
+  }
+}
+}  // namespace
+
+extern "C" int mfk_attn_fwd_f32(const float* qkv, float* out, int N, int T, int heads, int causal, void* stream) {
+  if (!qkv || !out || N <= 0 || T <= 0 || T > 512 || heads <= 0) return MFK_EARG;
+  const size_t smem = ((size_t)T * 65 + (size_t)T * 64 + (size_t)F32_WARPS * T) * sizeof(float);
+  dim3 grid((T + F32_QBLK - 1) / F32_QBLK, heads, N);
+  cudaError_t e;
+  if (causal) {
+    e = cudaFuncSetAttribute(attn_fwd_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_fwd_f32_kernel<true><<<grid, F32_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(qkv, out, T, heads);
+  } else {
+    e = cudaFuncSetAttribute(attn_fwd_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_fwd_f32_kernel<false><<<grid, F32_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(qkv, out, T, heads);
+  }
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}

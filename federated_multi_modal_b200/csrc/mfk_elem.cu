@@ -421,6 +421,32 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ x, bf16* __restric
   o[2 * D + c] = hi;
 }
 
+// QuickGELU in fp32 (exact sigmoid) followed by the hi | lo | hi split: the activation of the fp32 mode.
+__global__ void quickgelu_split_bf16x3_kernel(const float* __restrict__ u, bf16* __restrict__ out, int rows, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * D) return;
+  const int r = (int)(i / D), c = (int)(i % D);
+  const float x = u[i];
+  const float v = x / (1.0f + expf(-1.702f * x));
+  const bf16 hi = __float2bfloat16_rn(v);
+  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = out + (size_t)r * 3 * D;
+  o[c] = hi;
+  o[D + c] = lo;
+  o[2 * D + c] = hi;
+}
+// im2col of the 16x16 / stride-16 patch embedding kept in fp32 (fp32 mode: split into bf16x3 afterwards)
+__global__ void im2col16_f32_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int S) {
+  const int G = S / 16;
+  const int patch = blockIdx.x;
+  const int b = patch / (G * G), pp = patch % (G * G), gy = pp / G, gx = pp % G;
+  for (int t = threadIdx.x; t < 192; t += blockDim.x) {
+    const int c = t / 64, ky = (t % 64) / 4, kx = (t % 4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * S + gy * 16 + ky) * S + gx * 16 + kx);
+    *reinterpret_cast<float4*>(out + (size_t)patch * 768 + c * 256 + ky * 16 + kx) = v;
+  }
+}
+
 // ============================================================================ small fp32 linears (prompt learner)
 // trainers/maple.py:194-215: y[m,N] = x[m,K] W[N,K]^T + b, m = n_ctx (tiny). One warp per output column.
 __global__ void linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
@@ -789,6 +815,23 @@ extern "C" int mfk_partial_reduce_grouped(const void* problems_dev, int n_proble
   if (!problems_dev || n_problems <= 0 || max_N <= 0) return MFK_EARG;
   launch_pdl(partial_reduce_grouped_kernel, dim3((max_N + 31) / 32, 2, n_problems), dim3(32, 32), 0, ST(stream),
              static_cast<const PartialReduceProblem*>(problems_dev));
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_quickgelu_split_bf16x3(const float* u, void* out_bf16, int rows, int D, void* stream) {
+  if (!u || !out_bf16 || rows <= 0 || D <= 0) return MFK_EARG;
+  const long long n = (long long)rows * D;
+  quickgelu_split_bf16x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(u, static_cast<bf16*>(out_bf16),
+                                                                                   rows, D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_patch_im2col_f32(const float* img, float* out, int B, int S, void* stream) {
+  if (!img || !out || B <= 0 || S % 16) return MFK_EARG;
+  const int G = S / 16;
+  im2col16_f32_kernel<<<B * G * G, 192, 0, ST(stream)>>>(img, out, B, S);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

@@ -59,6 +59,7 @@ class MapleEngine:
         self.n, self.J, self.patch = n_ctx, depth, patch
         self.trainable = trainable
         sd = {k: v for k, v in state_dict.items() if not k.startswith("clip_model2.")}
+        self._sd_src = sd if share_from is None else share_from._sd_src  # fp32 mode re-reads frozen weights exactly
         self.tok = tokenized_prompts.clone().cpu()
         self.eot = self.tok.argmax(-1)
         self.C = self.tok.shape[0]
@@ -472,12 +473,14 @@ class MapleEngine:
                                self.Tv, self.n)
         self.vx0 = x0
 
-    def _features(self, tw: _Tower, xout, rows, ln_g, ln_b, projT, name, R, train):
+    def _features(self, tw: _Tower, xout, rows, ln_g, ln_b, projT, name, R, train, rowidx=None):
+        """ln_post / ln_final on the R consumed rows (xout compact [R, D], or full with ``rowidx`` gathering them)
+        + split-precision projection to the joint embedding."""
         y = self._buf(name + ".y", (R, tw.D), F32)
         y3 = self._buf(name + ".y3", (R, 3 * tw.D), BF16)
         xs = self._buf(name + ".xs", (R, tw.D), F32)
         stat = self._buf(name + ".st", (2, R), F32)
-        ops.layernorm_fwd(xout, ln_g, ln_b, y_f32=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
+        ops.layernorm_fwd(xout, ln_g, ln_b, rowidx=rowidx, y_f32=y, x_save=xs, mean=stat[0], rstd=stat[1], M=R)
         # split-precision head (hi/lo bf16, one GEMM of depth 3D): keeps ~16 mantissa bits in the features
         ops.split_bf16x3(y, y3)
         feat = self._buf(name + ".feat", (R, self.E), F32)
@@ -513,14 +516,21 @@ class MapleEngine:
 
     # ------------------------------------------------------------------ public: inference
     @torch.no_grad()
-    def logits(self, img: torch.Tensor, cache_text: bool = True, shard_classes: bool = False) -> torch.Tensor:
+    def logits(self, img: torch.Tensor, cache_text: bool = True, shard_classes: bool = False,
+               precision: str = "bf16") -> torch.Tensor:
         """Eval path of CustomCLIP.forward (trainers/maple.py:381): returns logits [B, C] (fp32).
+        ``precision="fp32"``: the parity mode of the contract (logits within 1e-3 of the reference's fp32 path) —
+        every GEMM runs with bf16x3 split operands on the same tcgen05 kernel, LayerNorm / softmax / QuickGELU / the
+        residual stream in fp32 (see _block_fwd_f32); slower, inference only.
         Text features are input independent and cached across eval batches until parameters change.
         ``shard_classes``: under torch.distributed each rank runs the text tower on C/world classes and the
         [C, E] feature matrix is all-gathered once; images stay data-parallel."""
+        assert precision in ("bf16", "fp32")
         img = img.to(self.dev, F32).contiguous()
         B = img.shape[0]
         self._prompt_learner_fwd()
+        if precision == "fp32":
+            return self._logits_f32(img)
         if not (cache_text and self._text_cache_valid):
             import torch.distributed as dist
             if shard_classes and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -537,13 +547,98 @@ class MapleEngine:
                 self._ft_cache = ft.clone()
             self._text_cache_valid = True
         fi, _, _ = self._image_features(img, False)
+        self._last_fi = fi
         out = torch.empty(B, self.C, device=self.dev, dtype=F32)
         ws = self._buf("head.ws", (ops.head_workspace_floats(B, self.C, self.E),), F32)
         ops.head_forward_backward(fi, self._ft_cache, self.logit_scale, None, out, None, None, None, ws)
         return out
 
+    # ------------------------------------------------------------------ fp32 mode (parity contract, inference only)
+    def _w3(self, tw: _Tower, l: int, lin: str) -> torch.Tensor:
+        """[N, 3K] hi|hi|lo split of a block weight (cached for frozen weights, rebuilt for trainable ones)."""
+        w = tw.w[l]
+        key = lin + ".w3"
+        if key not in w or lin + ".master" in w:
+            src = w[lin + ".master"] if lin + ".master" in w else self._frozen_f32(tw, l, lin)
+            w[key] = self._split_b(src)
+        return w[key]
+
+    def _frozen_f32(self, tw: _Tower, l: int, lin: str) -> torch.Tensor:
+        # frozen weights are fp16 values in the reference: their bf16 copy is NOT exact, so the fp32 originals are kept
+        return self._sd_src[f"{tw.name}.transformer.resblocks.{l}.{_lin_keys(lin)[0]}"].to(self.dev, F32)
+
+    def _split_a(self, x: torch.Tensor, name: str) -> torch.Tensor:
+        out = self._buf(name, (x.shape[0], 3 * x.shape[1]), BF16)
+        ops.split_bf16x3(x, out)
+        return out
+
+    def _block_fwd_f32(self, tw: _Tower, l: int, x1: torch.Tensor, x1n: torch.Tensor):
+        """ResidualAttentionBlock_MaPLe.forward (clip/model.py:350-351) in fp32 mode; x1 -> x1n (both fp32 [M, D])."""
+        w, M, D = tw.w[l], tw.M, tw.D
+        pre = f"{tw.name}.f32."
+        hf = self._buf(pre + "hf", (M, D), F32)
+        x2 = self._buf(pre + "x2", (M, D), F32)
+        qkv = self._buf(pre + "qkv", (M, 3 * D), F32)
+        att = self._buf(pre + "att", (M, D), F32)
+        u = self._buf(pre + "u", (M, 4 * D), F32)
+        ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_f32=hf)
+        ops.gemm(self._split_a(hf, pre + "a3"), self._w3(tw, l, "attn.in_proj"), bias=w["attn.in_proj.b"], out_f32=qkv)
+        ops.attn_fwd_f32(qkv, att, tw.N, tw.T, tw.heads, tw.causal)
+        ops.gemm(self._split_a(att, pre + "a3"), self._w3(tw, l, "attn.out_proj"), bias=w["attn.out_proj.b"],
+                 residual=x1, out_f32=x2)
+        ops.layernorm_fwd(x2, w["ln_2.g"], w["ln_2.b"], y_f32=hf)
+        ops.gemm(self._split_a(hf, pre + "a3"), self._w3(tw, l, "mlp.c_fc"), bias=w["mlp.c_fc.b"], out_f32=u)
+        act3 = self._buf(pre + "act3", (M, 12 * D), BF16)
+        ops.quickgelu_split_bf16x3(u, act3)
+        ops.gemm(act3, self._w3(tw, l, "mlp.c_proj"), bias=w["mlp.c_proj.b"], residual=x2, out_f32=x1n)
+
+    def _tower_fwd_f32(self, tw: _Tower, deep: List[torch.Tensor], row0: int, x: torch.Tensor) -> torch.Tensor:
+        bufs = [x, self._buf(f"{tw.name}.f32.xb", tuple(x.shape), F32)]
+        for l in range(tw.L):
+            xin, xout = bufs[l % 2], bufs[(l + 1) % 2]
+            if l >= 1 and (l - 1) < len(deep):
+                ops.prompt_splice_fwd(xin, deep[l - 1], tw.N, tw.T, row0, self.n)
+            self._block_fwd_f32(tw, l, xin, xout)
+        return bufs[tw.L % 2]
+
+    def _logits_f32(self, img: torch.Tensor) -> torch.Tensor:
+        p, B = self.p, img.shape[0]
+        # ---- text tower (all 77 positions are not needed: rows after EOT are dead under the causal mask)
+        tw = self.txt
+        tw.N, tw.T, tw.M = self.C, self.Te, self.C * self.Te
+        xt = self._buf("txt.f32.x", (tw.M, tw.D), F32)
+        ops.text_assemble(self.prefix, p["prompt_learner.ctx"], self.suffix, self.tpos, xt, self.C, self.Te, self.n,
+                          self.Tfull)
+        xt = self._tower_fwd_f32(tw, self.deep_text, 1, xt)
+        ft, _, _ = self._features(tw, xt, None, p["text_encoder.ln_final.weight"], p["text_encoder.ln_final.bias"],
+                                  self.tproj_T, "txt32", self.C, False, rowidx=self.eot_rows)
+        # ---- vision tower
+        tw = self.vis
+        tw.N, tw.T, tw.M = B, self.Tv, B * self.Tv
+        colf = self._buf("vis.f32.col", (B * self.P, 3 * self.patch * self.patch), F32)
+        tok = self._buf("vis.f32.tok", (B * self.P, tw.D), F32)
+        ops.patch_im2col_f32(img, colf)
+        if getattr(self, "_conv_w3", None) is None:
+            self._conv_w3 = self._split_b(self._sd_src["image_encoder.conv1.weight"].to(self.dev, F32).reshape(tw.D, -1))
+        ops.gemm(self._split_a(colf, "vis.f32.col3"), self._conv_w3, out_f32=tok)
+        xv = self._buf("vis.f32.x", (tw.M, tw.D), F32)
+        st = self._buf("vis.f32.st", (2, tw.M), F32)
+        ops.vis_assemble_lnpre(tok, self.cls, self.vpos, self.shared, p["image_encoder.ln_pre.weight"],
+                               p["image_encoder.ln_pre.bias"], None, xv, st[0], st[1], B, self.Tv, self.n)
+        xv = self._tower_fwd_f32(tw, self.deep_vis, self.Tv - self.n, xv)
+        key = f"cls_rows{B}"
+        if key not in self._bufs:
+            self._bufs[key] = (torch.arange(B, device=self.dev, dtype=torch.int32) * self.Tv).contiguous()
+        fi, _, _ = self._features(tw, xv, None, p["image_encoder.ln_post.weight"], p["image_encoder.ln_post.bias"],
+                                  self.vproj_T, "vis32", B, False, rowidx=self._bufs[key])
+        self._last_fi = fi
+        out = torch.empty(B, self.C, device=self.dev, dtype=F32)
+        ws = self._buf("head.ws", (ops.head_workspace_floats(B, self.C, self.E),), F32)
+        ops.head_forward_backward(fi, ft, self.logit_scale, None, out, None, None, None, ws)
+        return out
+
     def last_image_features(self) -> torch.Tensor:
-        return self._bufs["vis.feat"].view(-1)[: self.vis.N * self.E].view(self.vis.N, self.E).clone()
+        return self._last_fi.clone()
 
     def _side_stream(self):
         st = self._bufs.get("__side_stream__")

@@ -159,6 +159,21 @@ def split_bf16x3(x, out):
     call("mfk_split_bf16x3", x, out, x.shape[0], x.shape[1], stream_ptr())
 
 
+def quickgelu_split_bf16x3(u, out):
+    _chk(u, F32, "u")
+    call("mfk_quickgelu_split_bf16x3", u, out, u.shape[0], u.shape[1], stream_ptr())
+
+
+def patch_im2col_f32(img, out):
+    _chk(img, F32, "img")
+    call("mfk_patch_im2col_f32", img, out, img.shape[0], img.shape[-1], stream_ptr())
+
+
+def attn_fwd_f32(qkv, out, N, T, heads, causal):
+    _chk(qkv, F32, "qkv"); _chk(out, F32, "out")
+    call("mfk_attn_fwd_f32", qkv, out, N, T, heads, int(causal), stream_ptr())
+
+
 def linear_small_fwd(x, W, b, y):
     call("mfk_linear_small_fwd", x, W, b, y, x.shape[0], W.shape[0], W.shape[1], stream_ptr())
 

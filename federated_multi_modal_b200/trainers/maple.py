@@ -266,7 +266,11 @@ class CustomCLIP(nn.Module):
             if not bool(torch.isfinite(loss)):
                 raise RuntimeError("NaN/Inf in total loss")  # trainers/maple.py:375-376
             return loss
-        logits = eng.logits(image)
+        # PREC == "fp32" (trainers/maple.py:438-439 calls clip_model.float()): inference runs the engine's fp32 mode
+        # (bf16x3 split-operand GEMMs, fp32 everything else; logits within 1e-3 of the reference's fp32 path).
+        # Training always uses the bf16 tensor-core path with fp32 master weights.
+        prec = "fp32" if str(getattr(self._cfg.TRAINER.MAPLE, "PREC", "bf16")) == "fp32" else "bf16"
+        logits = eng.logits(image, precision=prec)
         if return_feature:  # kept for signature compatibility with upstream MaPLe
             return logits, eng.last_image_features()
         return logits

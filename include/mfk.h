@@ -135,6 +135,13 @@ int mfk_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
  * B operand is packed [hi | hi | lo]; one mfk_gemm_bf16 of depth 3D then carries ~16 mantissa bits. Used for the
  * feature heads (`x @ proj`, clip/model.py:569-570; `@ text_projection`, trainers/maple.py:76).        */
 int mfk_split_bf16x3(const float* x, void* out_bf16, int rows, int D, void* stream);
+/* fp32 mode (parity contract: logits within 1e-3 of the reference's fp32 path; inference only). Every GEMM runs
+ * on the same tcgen05 kernel with hi|lo|hi x hi|hi|lo split operands (K -> 3K, fp32 out); these are the pieces in
+ * between: exact-sigmoid QuickGELU + split (clip/model.py:162-164), fp32 im2col (clip/model.py:514) and an fp32
+ * SIMT attention core (nn.MultiheadAttention, clip/model.py:303-305; qkv fp32 [N*T, 3D] -> out fp32 [N*T, D]). */
+int mfk_quickgelu_split_bf16x3(const float* u, void* out_bf16, int rows, int D, void* stream);
+int mfk_patch_im2col_f32(const float* img, float* out, int B, int S, void* stream);
+int mfk_attn_fwd_f32(const float* qkv, float* out, int N, int T, int heads, int causal, void* stream);
 
 /* ------------------------------------------------------------------ prompt-learner projections (fp32)
  * y[m,N] = x[m,K] W[N,K]^T + b (trainers/maple.py:194-215; m = n_ctx) and its backward.               */

@@ -39,6 +39,21 @@ def test_logits_vs_reference_golden(c1, truncate):
     assert torch.equal(eng.logits(img.cuda()).cpu(), lg)
 
 
+def test_fp32_mode_logits_vs_reference_golden(c1):
+    """north_star tolerance for the fp32 mode: logits within 1e-3 (relative to max |logit|) of the reference's
+    fp32 path — bf16x3 split-operand GEMMs on the tcgen05 kernel, fp32 LayerNorm / attention / QuickGELU."""
+    G, sd, tok, img, lab = c1
+    eng = MapleEngine(sd, tok)
+    lg = eng.logits(img.cuda(), precision="fp32").cpu()
+    ref = G["logits_eval"]
+    rel = _rel(lg, ref)
+    print("fp32-mode engine vs fp32-ref logits: max rel err", rel)
+    assert rel < 1e-3
+    assert torch.equal(lg.argmax(1), ref.argmax(1))
+    # the fp32 mode is an inference-only side path: the bf16 path still works afterwards and is unchanged
+    assert _rel(eng.logits(img.cuda()).cpu(), ref) < 2e-2
+
+
 def test_forward_backward_vs_oracle_and_golden(c1):
     G, sd, tok, img, lab = c1
     eng = MapleEngine(sd, tok, text_truncate=True)

@@ -174,6 +174,16 @@ def test_attention_fwd_bwd(N, T, heads, causal, impl):
     assert err < 3e-2 * max(1.0, x.grad.abs().max().item()), err
 
 
+@pytest.mark.parametrize("N,T,heads,causal", [(3, 199, 12, False), (5, 10, 8, True), (2, 77, 8, True)])
+def test_attention_fp32_mode(N, T, heads, causal):
+    D = heads * 64
+    qkv = rnd(N * T, 3 * D, seed=11)
+    out = torch.empty(N * T, D, device=DEV)
+    ops.attn_fwd_f32(qkv, out, N, T, heads, causal)
+    o_ref, _, _ = _attn_ref(qkv, N, T, heads, causal)
+    assert (out - o_ref).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("M,D", [(6368, 768), (770, 512), (37, 768), (5, 128)])
 def test_layernorm_fwd_bwd(M, D):
     x = rnd(M, D, std=2.0, seed=11) + 0.5
