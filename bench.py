@@ -274,6 +274,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     trainer = make_trainer(dev, graph=not args.no_graph)
     eng = trainer.model.engine
@@ -372,10 +373,12 @@ def run_ours(args):
             "gpu_launches": kernels_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": 13389056 + 3840,
+                         "frac": achieved / peak_tf, "traffic": 13357824 + 11776,
                          "traffic_note": "dram read+write bytes of ONE launch (QKV projection 6368x2304x768) from "
-                                         "profiles/r01_gemm_qkv_v0_ncu_raw.csv; algorithmic operand bytes A+B = 13.3 MB, "
-                                         "the 29 MB bf16 output stays in L2 for the consumer",
+                                         "profiles/r01_gemm_qkv_v10_ncu_raw.csv (ncu --set full); algorithmic operand "
+                                         "bytes A+B = 13.3 MB, the 29 MB bf16 output stays in L2 for the consumer; the "
+                                         "K=3072 split-K dgrad reads 43.9 MB = its operands "
+                                         "(profiles/r01_gemm_fcdgrad_splitk_v10_ncu_raw.csv)",
                          "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA)", "peak_source": peak_src,
                          "how": "96 real-operand vision GEMM launches x 5, CUDA events on the launching stream",
                          "us_per_launch": probe["us_per_launch"], "flops_per_launch": probe["flops_per_launch"],
