@@ -445,6 +445,7 @@ struct AttnTcParams {
   int T, Tk, heads, m_tiles, total_items;
   float c1;  // softmax scale * log2(e)
   long long* trace;  // optional debug: clock64 stamps of CTA 0, softmax warp 0 (tools/attn_trace.py fwd); NULL in production
+  unsigned smem_bytes;  // dynamic shared memory given to the launch
 };
 #define FTRC()                                                                                  \
   do {                                                                                          \
@@ -454,12 +455,33 @@ struct AttnTcParams {
 // Work unit = one (sequence, head): K and V are loaded once and shared by its (<= 2) 128-query tiles, whose S/O
 // accumulators use the two 256-column TMEM buffers. Q+K of the next unit are fetched as soon as this unit's QK^T
 // MMAs have retired and V is double-buffered, so TMA latency is hidden behind a whole unit of softmax work.
+// Two softmax warp groups (8 warps each), one per query tile of the unit: while one group is in its MUFU-bound
+// exp pass the other runs its TMEM-latency-bound max pass, waits for its P V, or stores its O tile, so the phases
+// of the two tiles of a (sequence, head) overlap instead of running back to back. Each group has its own MMA-issuing
+// thread (S = Q K^T on tmem_free, O = P V on p_full) and a third thread refills Q/K and V as soon as both groups'
+// MMAs on them have retired, so a group never waits on the other group's progress except through those buffers.
+// 16 + 3 warps = 608 threads: 5 warps share one scheduler's register file -> at most 96 registers per thread.
+constexpr int FWD_GROUPS = 2;
+constexpr int FWD_THREADS = (FWD_GROUPS * TC_SOFTMAX_WARPS + 3) * 32;  // + MMA issuer per group + TMA loader
+
 template <bool CAUSAL>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __maxnreg__(96)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw_tc[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  // barriers and the max / sum exchange slots come first, the swizzled tiles after them at the next 1024-byte
+  // boundary: for T = 256 the tiles alone take 224 KB and the total must stay within the 227 KB CTA limit
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw_tc);
+  uint64_t* qk_full = bars;         // [1]
+  uint64_t* v_full = bars + 1;      // [1]
+  uint64_t* s_full = bars + 3;      // [2] per query tile / group
+  uint64_t* o_full = bars + 5;      // [2]
+  uint64_t* tmem_free = bars + 7;   // [2]
+  uint64_t* p_full = bars + 9;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* sx = reinterpret_cast<float*>(smem_raw_tc + 128);  // [2 groups][2 halves][128 rows] max / sum exchange
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 128 + 2048 + 1023) &
+                                             ~uintptr_t(1023));
   const int Tk = p.Tk, D = p.heads * HD, NT = p.m_tiles;
   const uint32_t kvBytes = (uint32_t)Tk * 128u, qBytes = (uint32_t)NT * 16384u;
   const int nkb = (Tk + 63) / 64;  // 64-key column blocks of P
@@ -467,24 +489,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sQ = smem;                       // [NT x 128 rows x 128 B]
   uint8_t* sK = sQ + qBytes;                // [Tk x 128 B]
   uint8_t* sV = sK + kvBytes;               // [Tk x 128 B]
-  uint8_t* sP = sV + kvBytes;               // [2][nkb][128 x 128 B]: P of tile g in buffer g & 1 (also stages O)
-  float* sx = reinterpret_cast<float*>(sP + 2 * (size_t)pBytes);  // [2 halves][128 rows] max / sum exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 256);
-  uint64_t* qk_full = bars;         // [1]
-  uint64_t* v_full = bars + 1;      // [1]
-  uint64_t* s_full = bars + 3;      // [2] per accumulator buffer (tile parity)
-  uint64_t* o_full = bars + 5;      // [2]
-  uint64_t* tmem_free = bars + 7;   // [2]
-  uint64_t* p_full = bars + 9;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint8_t* sP = sV + kvBytes;               // [2 groups][nkb][128 x 128 B]: P of the group's tile (also stages its O)
+  if (threadIdx.x == 0 && (sP + 2 * (size_t)pBytes) - smem_raw_tc > (ptrdiff_t)p.smem_bytes) __trap();  // layout fits
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kCtl = FWD_GROUPS * TC_SOFTMAX_WARPS;  // control warp
   const int n_units = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  // Tiles are numbered g = unit * NT + query tile over the whole CTA; tile g uses accumulator / P buffer g & 1 and the
-  // barrier phase (g >> 1) & 1, so consecutive tiles always alternate buffers (also when NT == 1).
-  const int n_tiles = n_units * NT;
 
-  if (warp == TC_SOFTMAX_WARPS) {
+  if (warp == kCtl) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
@@ -515,8 +527,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     n = w / p.heads;
   };
 
-  if (warp == TC_SOFTMAX_WARPS) {
-    // ============================ control: TMA loads + MMA issue (one thread) ============================
+  if (warp == kCtl + 2) {
+    // ============================ loader: TMA loads of Q/K and V (one thread) ============================
     if (lane == 0) {
       auto issue_qk = [&](int u) {
         int n, h;
@@ -531,123 +543,72 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_arrive_expect_tx(v_full, kvBytes);
         tma_load_2d(&tmKV, v_full, sV, 2 * D + h * HD, n * p.T);
       };
-      const uint32_t idesc_s = umma_idesc_bf16(128, Tk, 0, 0);
-      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-      const int ksteps = Tk / 16;
-      // Event order seen by this thread (softmax warps: pass(g) -> p_full(g) -> epilogue(g - 1) frees the accumulator
-      // that tile g + 1 will use): PV(g) on p_full(g), then S(g + 1) on tmem_free; Q / K of the next unit are fetched
-      // as soon as the unit's last S has retired, V once its last P V has.
-      auto issue_s = [&](int t) {
-        const int u = t / NT, mt = t % NT, b = t & 1;
-        if (mt == 0) mbar_wait(qk_full, (uint32_t)u & 1u);
-        mbar_wait(&tmem_free[b], (((uint32_t)t >> 1) & 1u) ^ 1u);  // epilogue of tile t - 2 drained this buffer
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ) + (uint32_t)mt * 16384u);
-        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc + 2ull * k, bdesc + 2ull * k, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[b]);
-        if (mt == NT - 1 && u + 1 < n_units) {  // every MMA that reads Q / K of unit u has been issued: refill
-          mbar_wait(&s_full[b], ((uint32_t)t >> 1) & 1u);
-          issue_qk(u + 1);
-        }
-      };
       if (n_units > 0) {
         issue_qk(0);
         issue_v(0);
-        issue_s(0);
       }
-      const uint32_t vbase = smem_u32(sV);
-      for (int g = 0; g < n_tiles; ++g) {
-        const int u = g / NT, mt = g % NT, b = g & 1;
-        // S of the NEXT tile first: its accumulator is freed by epilogue(g - 1), which the softmax warps run right
-        // after handing P(g) over, so S(g + 1) is complete by the time they come back for it; PV(g) is not needed
-        // before epilogue(g), a whole softmax later.
-        if (g + 1 < n_tiles) issue_s(g + 1);
-        if (mt == 0 && u > 0) {  // V is single-buffered: the previous unit's last P V must have retired
-          mbar_wait(&o_full[(g - 1) & 1], ((uint32_t)(g - 1) >> 1) & 1u);
-          issue_v(u);
-        }
-        mbar_wait(&p_full[b], ((uint32_t)g >> 1) & 1u);
-        if (mt == 0) mbar_wait(v_full, (uint32_t)u & 1u);
-        tc_fence_after();
-        const uint32_t pbase = smem_u32(sP) + (uint32_t)b * pBytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t adesc = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
-          const uint64_t bdesc = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
-          umma_bf16(tmem_base + (uint32_t)b * 256u, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(&o_full[b]);
+      for (int u = 0; u + 1 < n_units; ++u) {
+        const uint32_t par = (uint32_t)u & 1u;
+        for (int mt = 0; mt < NT; ++mt) mbar_wait(&s_full[mt], par);   // every S MMA on Q/K of unit u retired
+        issue_qk(u + 1);
+        for (int mt = 0; mt < NT; ++mt) mbar_wait(&o_full[mt], par);   // every P V MMA on V of unit u retired
+        issue_v(u + 1);
       }
     }
     __syncwarp();
-  } else {
-    // ============================ softmax + epilogue warps ============================
-    // Software pipeline over tiles: softmax(g) -> P(g) handed to the tensor core -> epilogue(g - 1). The P V MMAs
-    // of tile g run under the epilogue of tile g - 1 and the softmax of tile g + 1 instead of being waited for.
-    const int q = warp & 3, half = warp >> 2;
+  } else if (warp >= kCtl) {
+    // ============================ MMA issuer of query tile mt (one thread per group) ============================
+    const int mt = warp - kCtl;
+    if (lane == 0 && mt < NT) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, Tk, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      const int ksteps = Tk / 16;
+      const uint32_t vbase = smem_u32(sV), pbase = smem_u32(sP) + (uint32_t)mt * pBytes;
+      const uint32_t d_tmem = tmem_base + (uint32_t)mt * 256u;
+      const uint64_t adesc = umma_desc_k_sw128(smem_u32(sQ) + (uint32_t)mt * 16384u);
+      const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sK));
+      for (int u = 0; u < n_units; ++u) {
+        const uint32_t par = (uint32_t)u & 1u;
+        mbar_wait(qk_full, par);
+        mbar_wait(&tmem_free[mt], par ^ 1u);  // the group's epilogue of the previous unit drained this buffer
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[mt]);
+        mbar_wait(v_full, par);
+        mbar_wait(&p_full[mt], par);
+        tc_fence_after();
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t pa = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
+          const uint64_t vb = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
+          umma_bf16(d_tmem, pa, vb, idesc_o, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[mt]);
+      }
+    }
+    __syncwarp();
+  } else if ((warp >> 3) < NT) {
+    // ============================ softmax + epilogue warp groups (group mt owns query tile mt) ============================
+    const int mt = warp >> 3, gw = warp & 7;          // group, warp inside the group
+    const int q = gw & 3, half = gw >> 2;
     const int rl = q * 32 + lane;  // row inside the 128-row tile == TMEM lane
     const uint32_t x7 = (uint32_t)rl & 7u;
+    float* gsx = sx + mt * 256;
+    const int pair_bar = 1 + mt * 4 + q, grp_bar = 9 + mt;
+    auto pair_sync_g = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(grp_bar) : "memory"); };
+    const uint32_t pbuf = smem_u32(sP) + (uint32_t)mt * pBytes;
+    const uint32_t prow = pbuf + (uint32_t)rl * 128u;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mt * 256u;
+    const int row = mt * 128 + rl;  // query index inside the sequence
+    const int kmax = CAUSAL ? min(p.T, row + 1) : p.T;  // keys [0, kmax) are visible
     int ftrc_n = 0;
-    // state of the tile whose epilogue is still pending
-    float l_prev = 0.f, mc_prev = 0.f;
-    auto epilogue = [&](int g, float l, float mc) {
-      const int u = g / NT, mt = g % NT, b = g & 1;
+    for (int u = 0; u < n_units; ++u) {
       int n, h;
       unit_coords(u, n, h);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * 256u;
-      mbar_wait(&o_full[b], ((uint32_t)g >> 1) & 1u);
-      tc_fence_after();
-      FTRC();  // O = P V ready
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      // O tile -> bf16 staged in this tile's (now idle) P buffer -> coalesced 128-byte row stores
-      const uint32_t obase = smem_u32(sP) + (uint32_t)b * pBytes;
-      {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(half * 32), r);
-        tc_wait_ld();
-        const uint32_t orow = obase + (uint32_t)rl * 128u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(orow + ((((uint32_t)half * 4 + j) ^ x7) << 4)),
-                       "r"(pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv)),
-                       "r"(pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv)),
-                       "r"(pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv)),
-                       "r"(pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv))
-                       : "memory");
-      }
-      const int row = mt * 128 + rl;
-      if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_free[b]);
-      asm volatile("bar.sync 5, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int idx = (int)threadIdx.x + m * (TC_SOFTMAX_WARPS * 32);
-        const int r_ = idx >> 3, ch = idx & 7;
-        if (mt * 128 + r_ < p.T) {
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(obase + (uint32_t)r_ * 128u + (((uint32_t)ch ^ ((uint32_t)r_ & 7u)) << 4)));
-          *reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T + mt * 128 + r_) * D + h * HD + ch * 8) = v;
-        }
-      }
-      // the buffer is overwritten by the P of tile g + 2: every thread must have read its part of the staged O
-      asm volatile("bar.sync 5, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
-      FTRC();  // epilogue done
-    };
-    for (int g = 0; g < n_tiles; ++g) {
-      const int mt = g % NT, b = g & 1;
-      const uint32_t par = ((uint32_t)g >> 1) & 1u;
-      const uint32_t prow = smem_u32(sP) + (uint32_t)b * pBytes + (uint32_t)rl * 128u;
-      const int row = mt * 128 + rl;  // query index inside the sequence
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * 256u;
-      const int kmax = CAUSAL ? min(p.T, row + 1) : p.T;  // keys [0, kmax) are visible
+      const uint32_t par = (uint32_t)u & 1u;
       FTRC();  // about to wait for S
-      mbar_wait(&s_full[b], par);
+      mbar_wait(&s_full[mt], par);
       tc_fence_after();
       FTRC();  // S ready
       float mx = -INFINITY;
@@ -666,57 +627,96 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
-      sx[half * 128 + rl] = mx;
-      pair_sync(q);
+      gsx[half * 128 + rl] = mx;
+      pair_sync_g();
       FTRC();  // pass 1 (row max) done
-      mx = fmaxf(mx, sx[(half ^ 1) * 128 + rl]);
+      mx = fmaxf(mx, gsx[(half ^ 1) * 128 + rl]);
       const float mc = (mx == -INFINITY) ? 0.f : mx * p.c1;
       float l = 0.f;
       for (int c = half * 32; c < Tk; c += 64) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tc_wait_ld();
-        float pv[32];
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[16];
         if (!CAUSAL && c + 32 <= p.T) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pv[j] = fast_exp2(__uint_as_float(r[j]) * p.c1 - mc);
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = fast_exp2(__uint_as_float(r[2 * j]) * p.c1 - mc);
+            const float e1 = fast_exp2(__uint_as_float(r[2 * j + 1]) * p.c1 - mc);
+            l4[j & 3] += e0 + e1;
+            pk[j] = pack_bf16(e0, e1);
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            pv[j] = (c + j < kmax) ? fast_exp2(__uint_as_float(r[j]) * p.c1 - mc) : 0.f;
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = (c + 2 * j < kmax) ? fast_exp2(__uint_as_float(r[2 * j]) * p.c1 - mc) : 0.f;
+            const float e1 = (c + 2 * j + 1 < kmax) ? fast_exp2(__uint_as_float(r[2 * j + 1]) * p.c1 - mc) : 0.f;
+            l4[j & 3] += e0 + e1;
+            pk[j] = pack_bf16(e0, e1);
+          }
         }
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 32; ++j) l4[j & 3] += pv[j];
         l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const uint32_t blk = prow + (uint32_t)(c >> 6) * 16384u;
         const uint32_t ch0 = (uint32_t)(c & 63) >> 3;  // first 16-byte chunk of this 32-column group: 0 or 4
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((ch0 + j) ^ x7) << 4)),
-                       "r"(pack_bf16(pv[8 * j], pv[8 * j + 1])), "r"(pack_bf16(pv[8 * j + 2], pv[8 * j + 3])),
-                       "r"(pack_bf16(pv[8 * j + 4], pv[8 * j + 5])), "r"(pack_bf16(pv[8 * j + 6], pv[8 * j + 7]))
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((ch0 + j) ^ x7) << 4)), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                        : "memory");
       }
-      pair_sync(q);                       // both warps have read the partner's max: the slot can be reused
-      sx[half * 128 + rl] = l;
+      pair_sync_g();                       // both warps have read the partner's max: the slot can be reused
+      gsx[half * 128 + rl] = l;
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(&p_full[mt]);
       FTRC();  // pass 2 (exp, P staged) done
-      pair_sync(q);
-      l += sx[(half ^ 1) * 128 + rl];
-      pair_sync(q);  // the partner has consumed this warp's partial sum before the next tile overwrites it
-      if (g > 0) epilogue(g - 1, l_prev, mc_prev);
-      l_prev = l;
-      mc_prev = mc;
+      pair_sync_g();
+      l += gsx[(half ^ 1) * 128 + rl];
+      // ---- epilogue: O = (P V) / l -> bf16 staged in this group's (now idle) P buffer -> coalesced row stores
+      mbar_wait(&o_full[mt], par);
+      tc_fence_after();
+      FTRC();  // O = P V ready
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(half * 32), r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + ((((uint32_t)half * 4 + j) ^ x7) << 4)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv))
+                       : "memory");
+      }
+      if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[mt]);
+      group_sync();
+      const int tid = (int)threadIdx.x & 255;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int idx = tid + m * 256;
+        const int r_ = idx >> 3, ch = idx & 7;
+        if (mt * 128 + r_ < p.T) {
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(pbuf + (uint32_t)r_ * 128u + (((uint32_t)ch ^ ((uint32_t)r_ & 7u)) << 4)));
+          *reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T + mt * 128 + r_) * D + h * HD + ch * 8) = v;
+        }
+      }
+      group_sync();  // the buffer is overwritten by the next unit's P: every thread must have read its part
+      FTRC();  // epilogue done
     }
-    if (n_tiles > 0) epilogue(n_tiles - 1, l_prev, mc_prev);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_SOFTMAX_WARPS) {
+  if (warp == kCtl) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -755,18 +755,20 @@ extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, in
                              128)) != MFK_OK)
     return rc;
   const int nkb = (p.Tk + 63) / 64;
-  const size_t smem = (size_t)p.m_tiles * 16384 + 2 * (size_t)p.Tk * 128 + 2 * (size_t)nkb * 16384 + 1024 + 128 + 1024;
+  // 128 (barriers) + 2048 (exchange slots) rounded up to the tiles' 1024-byte alignment, then Q, K, V, 2 x P
+  const size_t smem = 3072 + (size_t)p.m_tiles * 16384 + 2 * (size_t)p.Tk * 128 + 2 * (size_t)nkb * 16384;
+  p.smem_bytes = (unsigned)smem;
   const int grid = p.total_items < g_attn_sms ? p.total_items : g_attn_sms;
   cudaError_t e;
   if (causal) {
     e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), smem, static_cast<cudaStream_t>(stream), tmQ, tmKV, p);
+    e = launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(FWD_THREADS), smem, static_cast<cudaStream_t>(stream), tmQ, tmKV, p);
     if (e != cudaSuccess) return (int)e;
   } else {
     e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), smem, static_cast<cudaStream_t>(stream), tmQ, tmKV, p);
+    e = launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(FWD_THREADS), smem, static_cast<cudaStream_t>(stream), tmQ, tmKV, p);
     if (e != cudaSuccess) return (int)e;
   }
   MFK_CHECK_LAUNCH();

@@ -16,12 +16,10 @@ ops.attn_fwd(qkv, out, lse, N, T, H, False)
 torch.cuda.synchronize()
 _lib.call("mfk_debug_set_attn_trace", None)
 t = [int(x) for x in buf.cpu()[:60] if int(x) > 0]
-# stamp order per loop iteration g: wait S(g), S ready(g), pass1(g), pass2(g) [, PV(g-1) ready, epilogue(g-1) done]
-names = ["wait S(g)", "S(g) ready", "pass1(g) max", "pass2(g) exp+stage", "PV(g-1) ready", "epilogue(g-1) done"]
+# stamp order of softmax group 0 per unit: wait S, S ready, pass1 (row max), pass2 (exp, P staged), PV ready, epilogue done
+names = ["wait S", "S ready", "pass1 max", "pass2 exp+stage", "PV ready", "epilogue done"]
 base = t[0]
-idx = [(0, k) for k in range(4)] + [(g, k) for g in range(1, 12) for k in range(6)]
 for i, v in enumerate(t):
-    g, k = idx[i]
-    if k == 0:
-        print(f"--- g = {g}")
-    print(f"  {names[k]:20s} {v - base:8d}  (+{v - (t[i - 1] if i else base)})")
+    if i % 6 == 0:
+        print(f"--- unit {i // 6} (group 0 = query tile 0)")
+    print(f"  {names[i % 6]:18s} {v - base:8d}  (+{v - (t[i - 1] if i else base)})")
