@@ -52,6 +52,7 @@ SIGNATURES = {
     "mfk_linear_small_bwd_grouped": [P, I, I, I, I, P],
     "mfk_repack_grouped": [P, I, I, P],
     "mfk_partial_reduce_grouped": [P, I, I, P],
+    "mfk_rrc_flip_normalize": [P, I, I, I, P, P, P, P, P, I, I, P],
     "mfk_head_workspace_floats": [I, I, I],
     "mfk_head_forward_backward": [P, P, P, P, P, P, P, P, P, I, I, I, P],
     "mfk_fedavg_reduce": [P, P, F, I, L, I, P, P, P, P],

@@ -607,6 +607,59 @@ __global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab, int
   }
 }
 
+
+// ============================================================================ training-time augmentation on the GPU
+// Dassl's build_transform for the reference's yaml (configs/trainers/MaPLe/*.yaml:8-13): RandomResizedCrop(224,
+// bicubic) -> RandomHorizontalFlip -> ToTensor -> Normalize(mean, std). The random draws (crop box, flip) stay on the
+// host (cheap, torch RNG: trainers/client_datamanager.py); this kernel does the pixel work for a whole batch: antialiased
+// bicubic resampling (a = -0.5, PIL / torch `antialias=True` weights) of the crop box to S x S, rounding to the
+// uint8 grid like the PIL / uint8-tensor pipeline does, mirror, /255 and normalisation. src uint8 [B,3,H,W].
+__device__ __forceinline__ float cubic_aa(float x) {
+  constexpr float a = -0.5f;
+  x = fabsf(x);
+  if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+  if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+  return 0.f;
+}
+__device__ __forceinline__ void aa_window(float scale, int o, int in_size, int& lo, int& n, float& center,
+                                          float& invscale, float& total) {
+  const float support = scale >= 1.f ? 2.f * scale : 2.f;
+  center = scale * (o + 0.5f);
+  invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  lo = max((int)(center - support + 0.5f), 0);
+  n = min((int)(center + support + 0.5f), in_size) - lo;
+  total = 0.f;
+  for (int j = 0; j < n; ++j) total += cubic_aa((j + lo - center + 0.5f) * invscale);
+}
+__global__ void rrc_flip_normalize_kernel(const uint8_t* __restrict__ src, int H, int W, const int* __restrict__ boxes,
+                                          const uint8_t* __restrict__ flip, const float* __restrict__ mean,
+                                          const float* __restrict__ stdv, float* __restrict__ out, int S,
+                                          int round_u8) {
+  const int b = blockIdx.z;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ox >= S || oy >= S) return;
+  const int top = boxes[4 * b], left = boxes[4 * b + 1], bh = boxes[4 * b + 2], bw = boxes[4 * b + 3];
+  const int sx = flip[b] ? S - 1 - ox : ox;  // the flip follows the resize: output column ox shows resized column sx
+  int x0, nx, y0, ny;
+  float cx, ix, tx, cy, iy, ty;
+  aa_window((float)bw / (float)S, sx, bw, x0, nx, cx, ix, tx);
+  aa_window((float)bh / (float)S, oy, bh, y0, ny, cy, iy, ty);
+  const float inv_tx = 1.f / tx, inv_ty = 1.f / ty;
+  for (int c = 0; c < 3; ++c) {
+    const uint8_t* base = src + (((size_t)b * 3 + c) * H + top) * W + left;
+    float acc = 0.f;
+    for (int j = 0; j < ny; ++j) {
+      const float wy = cubic_aa((j + y0 - cy + 0.5f) * iy) * inv_ty;
+      const uint8_t* rowp = base + (size_t)(y0 + j) * W + x0;
+      float racc = 0.f;
+      for (int i = 0; i < nx; ++i) racc += cubic_aa((i + x0 - cx + 0.5f) * ix) * (float)rowp[i];
+      acc += wy * (racc * inv_tx);
+    }
+    if (round_u8) acc = fminf(fmaxf(rintf(acc), 0.f), 255.f);
+    out[(((size_t)b * 3 + c) * S + oy) * S + ox] = (acc * (1.f / 255.f) - mean[c]) / stdv[c];
+  }
+}
+
 }  // namespace
 
 // ================================================================================ C ABI
@@ -832,6 +885,18 @@ extern "C" int mfk_patch_im2col_f32(const float* img, float* out, int B, int S, 
   if (!img || !out || B <= 0 || S % 16) return MFK_EARG;
   const int G = S / 16;
   im2col16_f32_kernel<<<B * G * G, 192, 0, ST(stream)>>>(img, out, B, S);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_rrc_flip_normalize(const void* src_u8, int B, int H, int W, const int* boxes, const void* flip_u8,
+                                      const float* mean, const float* stdv, float* out, int S, int round_u8,
+                                      void* stream) {
+  if (!src_u8 || !boxes || !flip_u8 || !mean || !stdv || !out || B <= 0 || H <= 0 || W <= 0 || S <= 0) return MFK_EARG;
+  dim3 block(32, 8), grid((S + 31) / 32, (S + 7) / 8, B);
+  rrc_flip_normalize_kernel<<<grid, block, 0, ST(stream)>>>(static_cast<const uint8_t*>(src_u8), H, W, boxes,
+                                                           static_cast<const uint8_t*>(flip_u8), mean, stdv, out, S,
+                                                           round_u8);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

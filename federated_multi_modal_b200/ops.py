@@ -218,6 +218,16 @@ def repack_grouped(table, total_tiles):
     call("mfk_repack_grouped", table, table.shape[0], total_tiles, stream_ptr())
 
 
+def rrc_flip_normalize(src_u8, boxes, flip, mean, std, out, round_u8=True):
+    """RandomResizedCrop (antialiased bicubic) + flip + ToTensor + Normalize of a uint8 [B,3,H,W] batch on the GPU;
+    boxes int32 [B,4] = (top, left, height, width), flip uint8 [B] (drawn on the host), out fp32 [B,3,S,S]."""
+    assert src_u8.is_cuda and src_u8.dtype == torch.uint8 and src_u8.is_contiguous() and src_u8.dim() == 4
+    assert boxes.dtype == torch.int32 and flip.dtype == torch.uint8 and out.dtype == F32 and out.is_contiguous()
+    B, _, H, W = src_u8.shape
+    call("mfk_rrc_flip_normalize", src_u8, B, H, W, boxes, flip, mean, std, out, out.shape[-1], int(round_u8),
+         stream_ptr())
+
+
 def head_workspace_floats(B, C, E) -> int:
     return call("mfk_head_workspace_floats", B, C, E)
 

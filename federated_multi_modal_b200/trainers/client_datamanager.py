@@ -25,6 +25,7 @@ class Datum:
 class _Loader:
     def __init__(self, items, batch_size, shuffle, drop_last, tfm, seed=0):
         self.items, self.bs, self.shuffle, self.drop_last, self.tfm = items, batch_size, shuffle, drop_last, tfm
+        self.gpu_aug = tfm if isinstance(tfm, GpuAugment) else None
         self._gen = torch.Generator().manual_seed(seed)
         self.dataset = items
 
@@ -37,12 +38,83 @@ class _Loader:
         order = torch.randperm(n, generator=self._gen).tolist() if self.shuffle else list(range(n))
         for b in range(len(self)):
             idx = order[b * self.bs:(b + 1) * self.bs]
+            if self.gpu_aug is not None:  # raw uint8 batch + host-drawn augmentation parameters; pixels on the GPU
+                raw = torch.stack([self.items[i].img for i in idx])
+                assert raw.dtype == torch.uint8, "GpuAugment expects uint8 [3,H,W] item images"
+                boxes, flip = self.gpu_aug.draw(len(idx), raw.shape[-2], raw.shape[-1])
+                lab = torch.tensor([self.items[i].label for i in idx], dtype=torch.long)
+                if torch.cuda.is_available():
+                    raw, lab, boxes, flip = raw.pin_memory(), lab.pin_memory(), boxes.pin_memory(), flip.pin_memory()
+                yield {"img_u8": raw, "rrc_box": boxes, "flip": flip, "label": lab, "augment": self.gpu_aug,
+                       "impath": [self.items[i].impath for i in idx]}
+                continue
             imgs = [self.items[i].img if self.tfm is None else self.tfm(self.items[i]) for i in idx]
             img = torch.stack(imgs)
             lab = torch.tensor([self.items[i].label for i in idx], dtype=torch.long)
             if torch.cuda.is_available():
                 img, lab = img.pin_memory(), lab.pin_memory()
             yield {"img": img, "label": lab, "impath": [self.items[i].impath for i in idx]}
+
+
+def sample_rrc_params(height: int, width: int, generator: torch.Generator, scale=(0.08, 1.0),
+                      ratio=(3.0 / 4.0, 4.0 / 3.0)):
+    """Crop box (top, left, h, w) drawn like torchvision.transforms.RandomResizedCrop.get_params — the transform
+    Dassl's build_transform uses for "random_resized_crop" (10 attempts, then the centre-crop fallback)."""
+    import math
+    area = height * width
+    log_ratio = (math.log(ratio[0]), math.log(ratio[1]))
+    for _ in range(10):
+        target_area = area * torch.empty(1).uniform_(scale[0], scale[1], generator=generator).item()
+        aspect = math.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1], generator=generator).item())
+        w = int(round(math.sqrt(target_area * aspect)))
+        h = int(round(math.sqrt(target_area / aspect)))
+        if 0 < w <= width and 0 < h <= height:
+            i = int(torch.randint(0, height - h + 1, (1,), generator=generator).item())
+            j = int(torch.randint(0, width - w + 1, (1,), generator=generator).item())
+            return i, j, h, w
+    in_ratio = float(width) / float(height)
+    if in_ratio < min(ratio):
+        w, h = width, int(round(width / min(ratio)))
+    elif in_ratio > max(ratio):
+        h, w = height, int(round(height * max(ratio)))
+    else:
+        w, h = width, height
+    return (height - h) // 2, (width - w) // 2, h, w
+
+
+class GpuAugment:
+    """Training transform of the reference's yaml (random_resized_crop bicubic + random_flip + normalize, configs/
+    trainers/MaPLe/vit_b16_c2_ep5_batch4_2ctx.yaml:8-13) with the pixel work on the GPU: the loader ships the raw
+    uint8 [B,3,H,W] batch (4x fewer host->device bytes than fp32 crops) plus the host-drawn crop boxes / flips, and
+    ``apply`` runs libmfk's mfk_rrc_flip_normalize on the device. PIL + DataLoader workers stop being the bottleneck
+    at >= 7 k images/s per GPU."""
+    MEAN = (0.48145466, 0.4578275, 0.40821073)
+    STD = (0.26862954, 0.26130258, 0.27577711)
+
+    def __init__(self, size: int = 224, scale=(0.08, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), flip_p: float = 0.5,
+                 mean=MEAN, std=STD, seed: int = 0):
+        self.size, self.scale, self.ratio, self.flip_p = size, scale, ratio, flip_p
+        self.mean, self.std = torch.tensor(mean, dtype=torch.float32), torch.tensor(std, dtype=torch.float32)
+        self._gen = torch.Generator().manual_seed(seed)
+        self._dev = {}
+
+    def draw(self, n: int, height: int, width: int):
+        boxes = torch.tensor([sample_rrc_params(height, width, self._gen, self.scale, self.ratio) for _ in range(n)],
+                             dtype=torch.int32)
+        flip = (torch.rand(n, generator=self._gen) < self.flip_p).to(torch.uint8)
+        return boxes, flip
+
+    def apply(self, img_u8: torch.Tensor, boxes: torch.Tensor, flip: torch.Tensor, out=None) -> torch.Tensor:
+        from .. import ops
+        dev = img_u8.device
+        if dev not in self._dev:
+            self._dev[dev] = (self.mean.to(dev), self.std.to(dev))
+        mean, std = self._dev[dev]
+        if out is None:
+            out = torch.empty(img_u8.shape[0], 3, self.size, self.size, device=dev, dtype=torch.float32)
+        ops.rrc_flip_normalize(img_u8.contiguous(), boxes.to(dev, non_blocking=True), flip.to(dev, non_blocking=True),
+                               mean, std, out)
+        return out
 
 
 class ClientDataManager:

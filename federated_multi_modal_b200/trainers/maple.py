@@ -351,6 +351,13 @@ class MaPLe(TrainerX):
 
     # ------------------------------------------------------------------ step
     def parse_batch_train(self, batch):
+        if isinstance(batch, dict) and "img_u8" in batch:
+            # GpuAugment loader (client_datamanager.GpuAugment): raw uint8 images + host-drawn crop boxes / flips;
+            # random_resized_crop + flip + normalize run on the device
+            raw = batch["img_u8"].to(self.device, non_blocking=True)
+            x = batch["augment"].apply(raw, batch["rrc_box"], batch["flip"])
+            y = batch["label"].to(self.device, non_blocking=True)
+            return x, y, batch.get("caption")
         x = batch["img"].to(self.device, non_blocking=True)
         y = batch["label"].to(self.device, non_blocking=True)
         return x, y, batch.get("caption") if isinstance(batch, dict) else None

@@ -168,6 +168,14 @@ typedef struct mfk_repack_problem {
 } mfk_repack_problem;
 int mfk_repack_grouped(const void* problems_dev, int n_problems, int total_tiles, void* stream);
 
+/* ------------------------------------------------------------------ training-time augmentation
+ * Dassl build_transform for the reference's yaml (configs/trainers/MaPLe/vit_b16_c2_ep5_batch4_2ctx.yaml:8-13):
+ * random_resized_crop (bicubic, antialiased like PIL) -> random_flip -> ToTensor -> normalize, for a whole batch.
+ * src uint8 [B,3,H,W]; boxes int32 [B,4] = (top, left, height, width) and flip uint8 [B] are drawn on the host;
+ * out fp32 [B,3,S,S]. round_u8 = 1 reproduces the uint8 rounding of the PIL / uint8-tensor pipeline.   */
+int mfk_rrc_flip_normalize(const void* src_u8, int B, int H, int W, const int* boxes, const void* flip_u8,
+                           const float* mean, const float* stdv, float* out, int S, int round_u8, void* stream);
+
 /* ------------------------------------------------------------------ logits + loss head (trainers/maple.py:325-372)
  * label == NULL: inference, only `logits` [B,C] is written. Otherwise also loss[1], d_img[B,E], d_txt[C,E].
  * ws: mfk_head_workspace_floats(B,C,E) floats.                                                         */

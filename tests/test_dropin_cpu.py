@@ -145,3 +145,17 @@ def test_partitioners():
     assert max(sizes) > 1.5 * min(sizes)  # label skew gives unequal clients
     d = partition_dataset_dirichlet(ds, 8, 0.5, 0)
     assert sum(len(p[0]) for p in d) == 700
+
+
+def test_rrc_param_sampling_matches_torchvision():
+    """sample_rrc_params draws from a torch.Generator exactly what torchvision's RandomResizedCrop.get_params
+    draws from the global RNG (same call sequence), so with equal seeds the crop boxes are identical."""
+    import torch
+    from torchvision.transforms import RandomResizedCrop
+    from federated_multi_modal_b200.trainers.client_datamanager import sample_rrc_params
+    img = torch.zeros(3, 200, 260)
+    g = torch.Generator().manual_seed(5)
+    torch.manual_seed(5)
+    for _ in range(50):
+        want = RandomResizedCrop.get_params(img, scale=[0.08, 1.0], ratio=[3.0 / 4.0, 4.0 / 3.0])
+        assert sample_rrc_params(200, 260, g) == tuple(want)

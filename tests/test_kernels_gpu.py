@@ -425,3 +425,33 @@ def test_check_finite_and_sgd():
         ops.sgd_step(p, g, mom, hp, norm)
         assert (g - pt.grad).abs().max().item() < 1e-6
         assert (p - pt.detach()).abs().max().item() < 1e-6
+
+
+def test_gpu_augmentation_matches_torchvision():
+    """mfk_rrc_flip_normalize == torchvision resized_crop(bicubic, antialias) -> hflip -> /255 -> normalize on uint8
+    tensors (the PIL-compatible pipeline Dassl's build_transform produces for the reference's yaml), to the uint8
+    grid: at most 1 LSB (1/255/std) on a vanishing fraction of pixels, exact elsewhere."""
+    import torchvision.transforms.functional as TF
+    from federated_multi_modal_b200.trainers.client_datamanager import GpuAugment
+    g = torch.Generator().manual_seed(3)
+    B, H, W, S = 6, 256, 256, 224
+    raw = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+    # smooth content as well as noise: low-pass half of the batch
+    raw[: B // 2] = torch.nn.functional.avg_pool2d(raw[: B // 2].float(), 9, 1, 4).round().to(torch.uint8)
+    aug = GpuAugment(size=S, seed=11)
+    boxes, flip = aug.draw(B, H, W)
+    flip[0], flip[1] = 1, 0
+    out = aug.apply(raw.cuda(), boxes, flip).cpu()
+    mean, std = torch.tensor(GpuAugment.MEAN)[:, None, None], torch.tensor(GpuAugment.STD)[:, None, None]
+    worst, n_off = 0.0, 0
+    for b in range(B):
+        t, l, h, w = [int(v) for v in boxes[b]]
+        r = TF.resized_crop(raw[b], t, l, h, w, [S, S], interpolation=TF.InterpolationMode.BICUBIC, antialias=True)
+        if int(flip[b]):
+            r = TF.hflip(r)
+        want = (r.float() / 255.0 - mean) / std
+        lsb = ((out[b] - want).abs() * std * 255.0)
+        worst = max(worst, lsb.max().item())
+        n_off += int((lsb > 0.5).sum())
+    assert worst <= 1.01, worst
+    assert n_off <= 2e-3 * B * 3 * S * S, n_off

@@ -106,6 +106,27 @@ def test_training_is_bit_reproducible_at_bench_batch():
     assert torch.equal(outs[0][1], outs[1][1])
 
 
+def test_gpu_augment_loader_feeds_trainer():
+    """ClientDataManager with the GpuAugment transform: raw uint8 items (EuroSAT-sized 64x64) -> random_resized_crop
+    + flip + normalize on the device inside parse_batch_train -> one fused training step."""
+    from federated_multi_modal_b200.trainers import Datum, GpuAugment
+    g = torch.Generator().manual_seed(0)
+    names = synth.synthetic_classnames(10)
+    items = [Datum(impath=f"synthetic://{i}", label=i % 10, classname=names[i % 10],
+                   img=torch.randint(0, 256, (3, 64, 64), generator=g, dtype=torch.uint8)) for i in range(16)]
+    cfg = synth.make_cfg()
+    dm = ClientDataManager(items, items[:4], items[:4], cfg, custom_tfm_train=GpuAugment(seed=1))
+    batch = next(iter(dm.train_loader))
+    assert batch["img_u8"].dtype == torch.uint8 and batch["rrc_box"].shape == (batch["img_u8"].shape[0], 4)
+    t = _trainer(False)
+    t.model.train()
+    x, y, _ = t.parse_batch_train(batch)
+    assert x.shape == (batch["img_u8"].shape[0], 3, 224, 224) and x.dtype == torch.float32 and x.is_cuda
+    assert torch.isfinite(x).all() and x.abs().max().item() < 3.0   # CLIP-normalised pixel range
+    out = t.forward_backward(batch)
+    assert out["loss"] > 0
+
+
 def test_maple_rejects_bad_input_like_reference():
     t = _trainer(False)
     img, lab = synth.make_batch(4, 10, 123)
