@@ -580,30 +580,46 @@ __global__ void partial_reduce_grouped_kernel(const PartialReduceProblem* __rest
 // ---- grouped fp32 [M,N] -> bf16 copy + bf16 transpose (refresh of the trainable block weights after an update)
 struct RepackProblem {  // mirrors mfk.h
   const float* in; bf16* out_t; bf16* copy; int M, N;
-  int tile0, tiles_n;  // first global 32x32 tile index of this problem; its tiles per row
+  int tile0, tiles_n;  // first global 64x64 tile index of this problem; its tiles per row
 };
-// grid.x = total number of 32x32 tiles over all problems: every block finds its problem by a short scan
+// grid.x = total number of 64x64 tiles over all problems: every block finds its problem by a short scan.
+// block (32, 8): float2 loads / bf16x2 stores (128-byte warp rows both for the copy and for the transpose).
 __global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab, int n_problems) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][65];
   int pi = 0;
   while (pi + 1 < n_problems && (int)blockIdx.x >= tab[pi + 1].tile0) ++pi;
   const RepackProblem pr = tab[pi];
   const int t = (int)blockIdx.x - pr.tile0;
-  const int n0 = (t % pr.tiles_n) * 32, m0 = (t / pr.tiles_n) * 32;
+  const int n0 = (t % pr.tiles_n) * 64, m0 = (t / pr.tiles_n) * 64;
   if (m0 >= pr.M) return;  // uniform per block
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int m = m0 + i, n = n0 + threadIdx.x;
-    float v = 0.f;
-    if (m < pr.M && n < pr.N) {
-      v = pr.in[(size_t)m * pr.N + n];
-      if (pr.copy) pr.copy[(size_t)m * pr.N + n] = __float2bfloat16_rn(v);
+  const bool even = (pr.N & 1) == 0 && (pr.M & 1) == 0;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int m = m0 + i, n = n0 + 2 * threadIdx.x;
+    float v0 = 0.f, v1 = 0.f;
+    if (m < pr.M) {
+      if (even && n + 1 < pr.N) {
+        const float2 v = *reinterpret_cast<const float2*>(pr.in + (size_t)m * pr.N + n);
+        v0 = v.x; v1 = v.y;
+        if (pr.copy) *reinterpret_cast<uint32_t*>(pr.copy + (size_t)m * pr.N + n) = pack_bf16(v0, v1);
+      } else {
+        if (n < pr.N) { v0 = pr.in[(size_t)m * pr.N + n]; if (pr.copy) pr.copy[(size_t)m * pr.N + n] = __float2bfloat16_rn(v0); }
+        if (n + 1 < pr.N) { v1 = pr.in[(size_t)m * pr.N + n + 1]; if (pr.copy) pr.copy[(size_t)m * pr.N + n + 1] = __float2bfloat16_rn(v1); }
+      }
     }
-    tile[i][threadIdx.x] = v;
+    tile[i][2 * threadIdx.x] = v0;
+    tile[i][2 * threadIdx.x + 1] = v1;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int n = n0 + i, m = m0 + threadIdx.x;
-    if (n < pr.N && m < pr.M) pr.out_t[(size_t)n * pr.M + m] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int n = n0 + i, m = m0 + 2 * threadIdx.x;
+    if (n >= pr.N) continue;
+    const float v0 = tile[2 * threadIdx.x][i], v1 = tile[2 * threadIdx.x + 1][i];
+    if (even && m + 1 < pr.M) {
+      *reinterpret_cast<uint32_t*>(pr.out_t + (size_t)n * pr.M + m) = pack_bf16(v0, v1);
+    } else {
+      if (m < pr.M) pr.out_t[(size_t)n * pr.M + m] = __float2bfloat16_rn(v0);
+      if (m + 1 < pr.M) pr.out_t[(size_t)n * pr.M + m + 1] = __float2bfloat16_rn(v1);
+    }
   }
 }
 

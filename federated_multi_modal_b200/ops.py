@@ -203,12 +203,12 @@ def linear_small_bwd_grouped(table, max_m, max_N, max_K):
 
 
 def repack_table(problems, device):
-    """(device table of mfk_repack_problem, total 32x32 tiles) from (master fp32 [M,N], out_t bf16 [N,M],
+    """(device table of mfk_repack_problem, total 64x64 tiles) from (master fp32 [M,N], out_t bf16 [N,M],
     copy bf16 [M,N]) triples."""
     rows, tile0 = [], 0
     for w, t, c in problems:
         M, N = w.shape
-        tm, tn = (M + 31) // 32, (N + 31) // 32
+        tm, tn = (M + 63) // 64, (N + 63) // 64
         rows.append([w.data_ptr(), t.data_ptr(), c.data_ptr(), M | (N << 32), tile0 | (tn << 32)])
         tile0 += tm * tn
     return torch.tensor(rows, dtype=torch.int64, device=device).contiguous(), tile0

@@ -164,7 +164,7 @@ int mfk_linear_small_bwd_grouped(const void* problems_dev, int n_problems, int m
  * copy[M,N] = bf16(in), out_t[N,M] = bf16(in)^T (the K-major operand of the dgrad GEMM).               */
 typedef struct mfk_repack_problem {
   const float* in; void* out_t; void* copy; int M, N;
-  int tile0, tiles_n;   /* first global 32x32 tile of this problem (ascending), ceil(N/32) */
+  int tile0, tiles_n;   /* first global 64x64 tile of this problem (ascending), ceil(N/64) */
 } mfk_repack_problem;
 int mfk_repack_grouped(const void* problems_dev, int n_problems, int total_tiles, void* stream);
 

@@ -334,7 +334,7 @@ def test_grouped_small_linear_and_repack_match_single_calls():
         assert torch.equal(pr["y"], y1) and torch.equal(pr["dW"], dW1)
         assert torch.equal(pr["db"], db1) and torch.equal(pr["dx"], dx1)
     # grouped repack == transpose_bf16 per matrix
-    ws = [rnd(96, 160, seed=70), rnd(512, 2048, seed=71)]
+    ws = [rnd(96, 160, seed=70), rnd(512, 2048, seed=71), rnd(37, 51, seed=72)]
     trip = [(w, torch.empty(w.shape[1], w.shape[0], device=DEV, dtype=BF16),
              torch.empty(w.shape, device=DEV, dtype=BF16)) for w in ws]
     ops.repack_grouped(*ops.repack_table(trip, DEV))
