@@ -30,6 +30,8 @@ SIGNATURES = {
     "mfk_attn_bwd_tc": [P, P, P, P, P, P, I, I, I, I, P],
     "mfk_attn_bwd_fused": [P, P, P, P, P, P, I, I, I, P],
     "mfk_layernorm_fwd": [P, P, P, P, P, P, P, P, P, I, I, F, P],
+    "mfk_layernorm_fwd_splice": [P, P, P, P, P, P, P, P, P, I, I, F, P, I, I, I, P],
+    "mfk_layernorm_bwd_splice": [P, I, P, P, P, P, P, P, P, P, P, P, I, I, I, P, I, I, I, P],
     "mfk_ln_bwd_ctas": [I],
     "mfk_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
     "mfk_colsum": [P, I, L, I, I, P, P, I, P],
@@ -38,6 +40,7 @@ SIGNATURES = {
     "mfk_text_assemble": [P, P, P, P, P, I, I, I, I, I, P],
     "mfk_prompt_splice_fwd": [P, P, I, I, I, I, I, P],
     "mfk_prompt_splice_bwd": [P, P, P, I, I, I, I, I, I, I, P],
+    "mfk_prompt_splice_bwd_batched": [P, L, P, L, I, I, I, I, I, I, I, P],
     "mfk_scatter_rows": [P, P, P, P, I, I, P],
     "mfk_gather_rows": [P, P, P, I, L, I, P],
     "mfk_transpose_bf16": [P, I, L, P, L, P, L, I, I, P],

@@ -47,9 +47,10 @@ __device__ __forceinline__ void ln_row_write(const float4 (&v)[VEC], float mean,
 
 template <int VEC>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ rowidx, const float* __restrict__ gamma,
+ln_fwd_kernel(float* __restrict__ x, const int* __restrict__ rowidx, const float* __restrict__ gamma,
               const float* __restrict__ beta, bf16* __restrict__ y16, float* __restrict__ y32,
-              float* __restrict__ xsave, float* __restrict__ mean_o, float* __restrict__ rstd_o, int M, float eps) {
+              float* __restrict__ xsave, float* __restrict__ mean_o, float* __restrict__ rstd_o, int M, float eps,
+              const float* __restrict__ prompt, int T, int row0, int n_ctx) {
   constexpr int D = 128 * VEC;
   pdl_trigger();
   pdl_wait();
@@ -57,10 +58,23 @@ ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ rowidx, const
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= M) return;
   const size_t src = rowidx ? (size_t)rowidx[row] : (size_t)row;
-  const float4* xr = reinterpret_cast<const float4*>(x + src * D);
+  float4* xr = reinterpret_cast<float4*>(x + src * D);
   float4 v[VEC];
+  // fused deep-prompt splice (clip/model.py:320-349): the n_ctx prompt rows of every sequence are overwritten with
+  // q16(prompt) on the way in, and written back so that the residual stream holds them too
+  const int tpos = prompt ? row % T - row0 : -1;
+  if (tpos >= 0 && tpos < n_ctx) {
+    const float4* pr = reinterpret_cast<const float4*>(prompt + (size_t)tpos * D);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) v[i] = xr[lane + 32 * i];
+    for (int i = 0; i < VEC; ++i) {
+      const float4 a = __ldg(pr + lane + 32 * i);
+      v[i] = make_float4(q16(a.x), q16(a.y), q16(a.z), q16(a.w));
+      xr[lane + 32 * i] = v[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = xr[lane + 32 * i];
+  }
   if (xsave) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) reinterpret_cast<float4*>(xsave + (size_t)row * D)[lane + 32 * i] = v[i];
@@ -82,7 +96,8 @@ template <int VEC, bool DY_BF16>
 __global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ mean_i,
               const float* __restrict__ rstd_i, const float* __restrict__ gamma, const float* g_in,
-              float* g_out, bf16* __restrict__ g16, float* __restrict__ partial, int M) {
+              float* g_out, bf16* __restrict__ g16, float* __restrict__ partial, int M,
+              float* __restrict__ gprompt, int T, int row0, int n_ctx) {
   constexpr int D = 128 * VEC;
   // per-warp dgamma / dbeta accumulators live in shared memory (lane-private entries, no synchronisation inside the
   // row loop): the 48 registers they used to take now hold the prefetched residual gradient, so one row costs ONE
@@ -116,6 +131,11 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
       r[i] = g_in ? reinterpret_cast<const float4*>(g_in + (size_t)row * D)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float mean = mean_i[row], rstd = rstd_i[row];
+    int prow = -1;  // row of gprompt [N, n_ctx, D] if this is a spliced prompt position
+    if (gprompt) {
+      const int tp = row % T - row0;
+      if (tp >= 0 && tp < n_ctx) prow = (row / T) * n_ctx + tp;
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -145,6 +165,12 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
       o.z = (d[i].z - s1 - xh[i].z * s2) * rstd;
       o.w = (d[i].w - s1 - xh[i].w * s2) * rstd;
       if (g_in) { o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w; }
+      if (prow >= 0) {
+        // fused backward of the deep-prompt splice: this row was overwritten by the prompt in the forward pass, so
+        // its gradient belongs to the prompt (summed over the batch later, in batch order) and nothing flows on
+        reinterpret_cast<float4*>(gprompt + (size_t)prow * D)[c4] = o;
+        o = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       reinterpret_cast<float4*>(g_out + (size_t)row * D)[c4] = o;
       if (g16) reinterpret_cast<uint2*>(g16 + (size_t)row * D)[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     }
@@ -312,9 +338,12 @@ __global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict
 // block (32 columns, 8 batch groups): group y sums sequences y, y+8, ... in order; groups are combined in order
 // 0..7 (for N <= 8 this is the plain sequential batch order of autograd's expand-backward).
 __global__ void splice_bwd_kernel(float* __restrict__ g, bf16* __restrict__ g16, float* __restrict__ dprompt, int N,
-                                  int T, int row0, int n_ctx, int D, int round16, int zero) {
+                                  int T, int row0, int n_ctx, int D, int round16, int zero, long long g_stride,
+                                  long long dp_stride) {
   pdl_trigger();
   pdl_wait();
+  g += (size_t)blockIdx.z * g_stride;  // batched over layers (blockIdx.z): one launch for every spliced layer
+  dprompt += (size_t)blockIdx.z * dp_stride;
   __shared__ float red[8][33];
   const int j = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -681,16 +710,29 @@ __global__ void rrc_flip_normalize_kernel(const uint8_t* __restrict__ src, int H
 // ================================================================================ C ABI
 #define ST(s) static_cast<cudaStream_t>(s)
 
+extern "C" int mfk_layernorm_fwd_splice(float* x, const int* rowidx, const float* gamma, const float* beta,
+                                        void* y_bf16, float* y_f32, float* x_save, float* mean, float* rstd, int M,
+                                        int D, float eps, const float* prompt, int T, int row0, int n_ctx,
+                                        void* stream);
 extern "C" int mfk_layernorm_fwd(const float* x, const int* rowidx, const float* gamma, const float* beta,
                                  void* y_bf16, float* y_f32, float* x_save, float* mean, float* rstd, int M, int D,
                                  float eps, void* stream) {
+  return mfk_layernorm_fwd_splice(const_cast<float*>(x), rowidx, gamma, beta, y_bf16, y_f32, x_save, mean, rstd, M, D,
+                                  eps, nullptr, 1, 0, 0, stream);
+}
+
+extern "C" int mfk_layernorm_fwd_splice(float* x, const int* rowidx, const float* gamma, const float* beta,
+                                        void* y_bf16, float* y_f32, float* x_save, float* mean, float* rstd, int M,
+                                        int D, float eps, const float* prompt, int T, int row0, int n_ctx,
+                                        void* stream) {
   if (!x || !gamma || !beta || M <= 0) return MFK_EARG;
   if (!y_bf16 && !y_f32) return MFK_EARG;
+  if (prompt && (rowidx || T <= 0 || row0 < 0 || n_ctx <= 0 || row0 + n_ctx > T)) return MFK_EARG;
   const int grid = (M + kLnWarps - 1) / kLnWarps;
   bf16* y16 = static_cast<bf16*>(y_bf16);
-  if (D == 768) launch_pdl(ln_fwd_kernel<6>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
-  else if (D == 512) launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
-  else if (D == 128) launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps);
+  if (D == 768) launch_pdl(ln_fwd_kernel<6>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
+  else if (D == 512) launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
+  else if (D == 128) launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
   else return MFK_ESHAPE;
   MFK_CHECK_LAUNCH();
   return MFK_OK;
@@ -701,19 +743,34 @@ extern "C" int mfk_ln_bwd_ctas(int M) {
   return g < 296 ? g : 296;  // 2 resident CTAs per SM on 148 SMs
 }
 
+extern "C" int mfk_layernorm_bwd_splice(const void* dy, int dy_is_bf16, const float* x, const float* mean,
+                                        const float* rstd, const float* gamma, const float* g_in, float* g_out,
+                                        void* g_out_bf16, float* dgamma, float* dbeta, float* partial_ws,
+                                        int accumulate, int M, int D, float* gprompt, int T, int row0, int n_ctx,
+                                        void* stream);
 extern "C" int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
                                  const float* gamma, const float* g_in, float* g_out, void* g_out_bf16,
                                  float* dgamma, float* dbeta, float* partial_ws, int accumulate, int M, int D,
                                  void* stream) {
+  return mfk_layernorm_bwd_splice(dy, dy_is_bf16, x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma, dbeta,
+                                  partial_ws, accumulate, M, D, nullptr, 1, 0, 0, stream);
+}
+
+extern "C" int mfk_layernorm_bwd_splice(const void* dy, int dy_is_bf16, const float* x, const float* mean,
+                                        const float* rstd, const float* gamma, const float* g_in, float* g_out,
+                                        void* g_out_bf16, float* dgamma, float* dbeta, float* partial_ws,
+                                        int accumulate, int M, int D, float* gprompt, int T, int row0, int n_ctx,
+                                        void* stream) {
   if (!dy || !x || !mean || !rstd || !gamma || !g_out || M <= 0) return MFK_EARG;
+  if (gprompt && (T <= 0 || row0 < 0 || n_ctx <= 0 || row0 + n_ctx > T)) return MFK_EARG;
   if ((dgamma || dbeta) && !partial_ws) return MFK_EARG;
   const int grid = mfk_ln_bwd_ctas(M);
   bf16* g16 = static_cast<bf16*>(g_out_bf16);
   float* part = (dgamma || dbeta) ? partial_ws : nullptr;
 #define LNB(V)                                                                                                     \
   do {                                                                                                             \
-    if (dy_is_bf16) launch_pdl(ln_bwd_kernel<V, true>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M); \
-    else launch_pdl(ln_bwd_kernel<V, false>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M);           \
+    if (dy_is_bf16) launch_pdl(ln_bwd_kernel<V, true>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M, gprompt, T, row0, n_ctx); \
+    else launch_pdl(ln_bwd_kernel<V, false>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), dy, x, mean, rstd, gamma, g_in, g_out, g16, part, M, gprompt, T, row0, n_ctx);           \
   } while (0)
   if (D == 768) LNB(6);
   else if (D == 512) LNB(4);
@@ -782,7 +839,18 @@ extern "C" int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int
   if (!g || !dprompt || row0 < 0 || row0 + n_ctx > T) return MFK_EARG;
   dim3 grid((D + 31) / 32, n_ctx);
   launch_pdl(splice_bwd_kernel, grid, dim3(32, 8), 0, ST(stream), g, static_cast<bf16*>(g_bf16), dprompt, N, T, row0,
-             n_ctx, D, round_fp16, zero_rows);
+             n_ctx, D, round_fp16, zero_rows, 0LL, 0LL);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_prompt_splice_bwd_batched(float* g, long long g_stride, float* dprompt, long long dp_stride,
+                                             int layers, int N, int T, int row0, int n_ctx, int D, int round_fp16,
+                                             void* stream) {
+  if (!g || !dprompt || layers <= 0 || row0 < 0 || row0 + n_ctx > T) return MFK_EARG;
+  dim3 grid((D + 31) / 32, n_ctx, layers);
+  launch_pdl(splice_bwd_kernel, grid, dim3(32, 8), 0, ST(stream), g, static_cast<bf16*>(nullptr), dprompt, N, T, row0,
+             n_ctx, D, round_fp16, 0, g_stride, dp_stride);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

@@ -272,7 +272,7 @@ class MapleEngine:
         self.deep_text: List[torch.Tensor] = []
         self.deep_vis: List[torch.Tensor] = []
         probs = []
-        dpr = lambda tw, i: self._buf(f"{tw.name}.dprompt{i}", (n, tw.D), F32)
+        dpr = lambda tw, i: self._dprompt_all(tw)[i]
         for i in range(nd):
             Wn = f"{pl}compound_prompt_projections.{i}"
             W, b = p[Wn + ".weight"], p[Wn + ".bias"]
@@ -298,6 +298,10 @@ class MapleEngine:
         self._pl_table = ops.small_linear_table(probs, self.dev)
         self._pl_keep = probs  # fixed-size buffers: _buf never reallocates them, so the pointers stay valid
 
+    def _dprompt_all(self, tw: _Tower) -> torch.Tensor:
+        """[J-1, n_ctx, D] gradients of the deep prompts of one tower (fixed address: the problem table points in)."""
+        return self._buf(f"{tw.name}.dprompt_all", (max(self.J - 1, 1), self.n, tw.D), F32)
+
     def _prompt_learner_fwd(self):
         """MultiModalPromptLearner.forward (trainers/maple.py:194-215): all projections in one grouped launch."""
         if getattr(self, "_pl_table", None) is None:
@@ -309,14 +313,15 @@ class MapleEngine:
         """(x1 in, x1 out, per-layer slot) — training keeps every layer, inference ping-pongs two buffers."""
         return (l, l + 1, l) if train else (l % 2, (l + 1) % 2, 0)
 
-    def _block_fwd(self, tw: _Tower, l: int, train: bool, rows=None):
+    def _block_fwd(self, tw: _Tower, l: int, train: bool, rows=None, splice=None):
         """rows (int32 [N]) is given for the LAST block only: everything after the attention core then runs on
         those gathered rows and the compact [N, D] result is returned."""
         ws, w = tw.ws, tw.w[l]
         si, so, s = self._slots(l, train)
         x1, x1n, x2 = ws["x1"][si], ws["x1"][so], ws["x2"][s]
         st = ws["stat"][l] if train else (None, None, None, None)
-        ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_bf16=ws["h"], mean=st[0], rstd=st[1])
+        # splice = (prompt, T, row0, n_ctx): the deep-prompt splice of this layer is fused into ln_1 (x1 updated in place)
+        ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_bf16=ws["h"], mean=st[0], rstd=st[1], splice=splice)
         qkv, att = ws["qkv"][s], ws["att"][s]
         ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=qkv, ws=tw.gemm_ws)
         ops.attn_fwd(qkv, att, ws["lse"][l] if train else None, tw.N, tw.T, tw.heads, tw.causal)
@@ -343,9 +348,8 @@ class MapleEngine:
         """Returns the compact [N, D] output rows (CLS / EOT) of the last block."""
         out = None
         for l in range(tw.L):
-            if l >= 1 and (l - 1) < len(deep):
-                ops.prompt_splice_fwd(tw.ws["x1"][self._slots(l, train)[0]], deep[l - 1], tw.N, tw.T, row0, self.n)
-            out = self._block_fwd(tw, l, train, rows if l == tw.L - 1 else None)
+            splice = (deep[l - 1], tw.T, row0, self.n) if (l >= 1 and (l - 1) < len(deep)) else None
+            out = self._block_fwd(tw, l, train, rows if l == tw.L - 1 else None, splice)
         return out
 
     def _wgrad(self, tw: _Tower, dy16, x16, dW, Nout, Kin):
@@ -354,12 +358,13 @@ class MapleEngine:
 
     # ------------------------------------------------------------------ LayerNorm backward with deferred dgamma/dbeta
     def _ln_bwd(self, tw: _Tower, dy, x, mean, rstd, gamma, *, g_in=None, g_out, g_out_bf16=None, dgamma=None,
-                dbeta=None, M=None):
+                dbeta=None, M=None, splice_grad=None):
         """LayerNorm backward whose per-CTA dgamma/dbeta partials go to this call's own slot of the tower's partial
         buffer; _ln_reduce() finishes every LayerNorm of the tower in one grouped launch (fixed order: the step's
         launch sequence is static, so slot k is always the same LayerNorm)."""
         if dgamma is None and dbeta is None:
-            ops.layernorm_bwd(dy, x, mean, rstd, gamma, g_in=g_in, g_out=g_out, g_out_bf16=g_out_bf16, M=M)
+            ops.layernorm_bwd(dy, x, mean, rstd, gamma, g_in=g_in, g_out=g_out, g_out_bf16=g_out_bf16, M=M,
+                              splice_grad=splice_grad)
             return
         D = x.shape[-1]
         rows = x.numel() // D if M is None else M
@@ -367,7 +372,7 @@ class MapleEngine:
         tw.ln_slot += 1
         part = tw.ws["lnp_all"][slot]
         ops.layernorm_bwd(dy, x, mean, rstd, gamma, g_in=g_in, g_out=g_out, g_out_bf16=g_out_bf16, dgamma=dgamma,
-                          dbeta=dbeta, partial_ws=part, M=M, defer=True)
+                          dbeta=dbeta, partial_ws=part, M=M, defer=True, splice_grad=splice_grad)
         tw.ln_pending.append((part, ops.ln_bwd_ctas(rows), D, dgamma, dbeta, False))
 
     def _ln_reduce(self, tw: _Tower):
@@ -407,7 +412,7 @@ class MapleEngine:
         ops.scatter_rows(g, rows, ws["g"], ws["g16"])
         ops.gather_rows(ws["dh_r"], rows, ws["dh"], scatter=True)
 
-    def _block_bwd(self, tw: _Tower, l: int, attn_only: bool = False):
+    def _block_bwd(self, tw: _Tower, l: int, attn_only: bool = False, splice_grad=None):
         """attn_only: the MLP / out-proj part was already done on gathered rows (_last_block_bwd_rows)."""
         ws, w, D, M = tw.ws, tw.w[l], tw.D, tw.M
         g, g16 = ws["g"], ws["g16"]
@@ -426,7 +431,7 @@ class MapleEngine:
                 ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
             self._ln_bwd(tw, ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
                               dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
-                              dbeta=G[pre + "ln_1.bias"] if ln_grads else None)
+                              dbeta=G[pre + "ln_1.bias"] if ln_grads else None, splice_grad=splice_grad)
             return
         # ---- MLP branch
         ops.gemm(g16, w["mlp.c_proj.wT"], act=2, aux=ws["u"][l], out_bf16=ws["du"], ws=tw.gemm_ws)
@@ -454,7 +459,7 @@ class MapleEngine:
             ops.colsum(ws["dqkv"], G[pre + "attn.in_proj_bias"], ws["csum"])
         self._ln_bwd(tw, ws["dh"], ws["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g, g_out_bf16=g16,
                           dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
-                          dbeta=G[pre + "ln_1.bias"] if ln_grads else None)
+                          dbeta=G[pre + "ln_1.bias"] if ln_grads else None, splice_grad=splice_grad)
 
     # ------------------------------------------------------------------ towers: embed + head rows
     def _vision_embed(self, img: torch.Tensor, train: bool):
@@ -661,18 +666,20 @@ class MapleEngine:
                           dgamma=G[lnname + ".weight"] if ln_grads else None,
                           dbeta=G[lnname + ".bias"] if ln_grads else None, M=R)
         self._last_block_bwd_rows(tw, rows)
-        got = {}
+        # Deep-prompt splices: ln_1 backward of a spliced layer diverts the gradient of the prompt rows to
+        # gprompt[l - 1] ([N, n, D]) and zeroes them in the stream; one batched launch then sums all layers over the
+        # batch (batch order, fp16-rounded like autograd through `.half()`).
+        ns = max(0, min(nd, tw.L - 1))                       # spliced layers 1 .. ns
+        gp = self._buf(f"{tw.name}.gprompt", (max(ns, 1), tw.N * n, D), F32)
+        dp_all = self._dprompt_all(tw)
         for l in reversed(range(tw.L)):
-            self._block_bwd(tw, l, attn_only=(l == tw.L - 1))
-            if l >= 1 and (l - 1) < nd:
-                dp = self._buf(f"{tw.name}.dprompt{l - 1}", (n, D), F32)
-                ops.prompt_splice_bwd(ws["g"], ws["g16"], dp, tw.N, tw.T, deep_row0, n, True, True)
-                got[l - 1] = dp
-        for i in range(nd):  # deep prompts beyond the tower depth are never spliced: zero gradient
-            if i not in got:
-                z = self._buf(f"{tw.name}.dprompt{i}", (n, D), F32)
-                z.zero_()
-                got[i] = z
+            sg = (gp[l - 1], tw.T, deep_row0, n) if 1 <= l <= ns else None
+            self._block_bwd(tw, l, attn_only=(l == tw.L - 1), splice_grad=sg)
+        if ns > 0:
+            ops.prompt_splice_bwd_batched(gp[:ns], dp_all[:ns], tw.N, n, 0, n, True)
+        if ns < nd:  # deep prompts beyond the tower depth are never spliced: zero gradient
+            dp_all[ns:].zero_()
+        got = {i: dp_all[i] for i in range(nd)}
         return got
 
     # ------------------------------------------------------------------ public: training step

@@ -75,11 +75,17 @@ def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal, impl: Op
 
 
 def layernorm_fwd(x, gamma, beta, *, rowidx=None, y_bf16=None, y_f32=None, x_save=None, mean=None, rstd=None,
-                  M=None, eps=1e-5):
+                  M=None, eps=1e-5, splice=None):
+    """splice = (prompt [n_ctx, D] fp32, T, row0, n_ctx): fused deep-prompt splice (x is updated in place)."""
     _chk(x, F32, "x")
     D = x.shape[-1]
     M = (rowidx.numel() if rowidx is not None else x.numel() // D) if M is None else M
-    call("mfk_layernorm_fwd", x, rowidx, gamma, beta, y_bf16, y_f32, x_save, mean, rstd, M, D, eps, stream_ptr())
+    if splice is None:
+        call("mfk_layernorm_fwd", x, rowidx, gamma, beta, y_bf16, y_f32, x_save, mean, rstd, M, D, eps, stream_ptr())
+    else:
+        prompt, T, row0, n_ctx = splice
+        call("mfk_layernorm_fwd_splice", x, rowidx, gamma, beta, y_bf16, y_f32, x_save, mean, rstd, M, D, eps, prompt,
+             T, row0, n_ctx, stream_ptr())
 
 
 def ln_bwd_ctas(M: int) -> int:
@@ -87,13 +93,20 @@ def ln_bwd_ctas(M: int) -> int:
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, g_in=None, g_out, g_out_bf16=None, dgamma=None, dbeta=None,
-                  partial_ws=None, accumulate=False, M=None, defer=False):
-    """defer: leave the per-CTA dgamma/dbeta partials in partial_ws (reduced later by partial_reduce_grouped)."""
+                  partial_ws=None, accumulate=False, M=None, defer=False, splice_grad=None):
+    """defer: leave the per-CTA dgamma/dbeta partials in partial_ws (reduced later by partial_reduce_grouped).
+    splice_grad = (gprompt [N, n_ctx, D] fp32, T, row0, n_ctx): fused backward of the deep-prompt splice."""
     D = x.shape[-1]
     M = x.numel() // D if M is None else M
-    call("mfk_layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma,
-         dbeta, partial_ws, int(accumulate) | (2 if defer else 0), M, D, stream_ptr(),
-         kernels=1 + ((dgamma is not None or dbeta is not None) and not defer))
+    flags = int(accumulate) | (2 if defer else 0)
+    k = 1 + ((dgamma is not None or dbeta is not None) and not defer)
+    if splice_grad is None:
+        call("mfk_layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, gamma, g_in, g_out, g_out_bf16, dgamma,
+             dbeta, partial_ws, flags, M, D, stream_ptr(), kernels=k)
+    else:
+        gp, T, row0, n_ctx = splice_grad
+        call("mfk_layernorm_bwd_splice", dy, int(dy.dtype == BF16), x, mean, rstd, gamma, g_in, g_out, g_out_bf16,
+             dgamma, dbeta, partial_ws, flags, M, D, gp, T, row0, n_ctx, stream_ptr(), kernels=k)
 
 
 def partial_reduce_table(problems, device) -> torch.Tensor:
@@ -133,6 +146,14 @@ def prompt_splice_fwd(x, prompt, N, T, row0, n_ctx):
 def prompt_splice_bwd(g, g_bf16, dprompt, N, T, row0, n_ctx, round_fp16=True, zero_rows=True):
     call("mfk_prompt_splice_bwd", g, g_bf16, dprompt, N, T, row0, n_ctx, g.shape[-1], int(round_fp16),
          int(zero_rows), stream_ptr())
+
+
+def prompt_splice_bwd_batched(g_all, dprompt_all, N, T, row0, n_ctx, round_fp16=True):
+    """g_all [layers, N*T, D] (or any per-layer tensor with row = sequence*T + t), dprompt_all [layers, n_ctx, D]:
+    dprompt[l, j] = sum over sequences of (fp16-rounded) g[l, b*T + row0 + j] in batch order, one launch."""
+    Lr, D = g_all.shape[0], g_all.shape[-1]
+    call("mfk_prompt_splice_bwd_batched", g_all, g_all.stride(0), dprompt_all, dprompt_all.stride(0), Lr, N, T, row0,
+         n_ctx, D, int(round_fp16), stream_ptr())
 
 
 def scatter_rows(dx, rowidx, g, g_bf16):

@@ -91,6 +91,17 @@ int mfk_layernorm_fwd(const float* x, const int* rowidx, const float* gamma, con
  * reduction). partial_ws: 2*D*mfk_ln_bwd_ctas(M) floats. g_in may alias g_out. `accumulate`: bit 0 adds into
  * dgamma/dbeta; bit 1 DEFERS the second stage — the per-CTA partials stay in partial_ws ([P][2][D], P =
  * mfk_ln_bwd_ctas(M)) and the caller reduces many LayerNorms at once with mfk_partial_reduce_grouped.          */
+/* Variants with the deep-prompt splice of ResidualAttentionBlock_MaPLe (clip/model.py:320-349) fused in:
+ * forward: rows t in [row0, row0+n_ctx) of every T-row sequence are first overwritten (also in x) with
+ * fp16-rounded prompt[t-row0]; backward: the gradient of those rows goes to gprompt [M/T, n_ctx, D] instead of
+ * g_out (which gets zeros there) — sum it over the batch with mfk_prompt_splice_bwd on that tensor.            */
+int mfk_layernorm_fwd_splice(float* x, const int* rowidx, const float* gamma, const float* beta, void* y_bf16,
+                             float* y_f32, float* x_save, float* mean, float* rstd, int M, int D, float eps,
+                             const float* prompt, int T, int row0, int n_ctx, void* stream);
+int mfk_layernorm_bwd_splice(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                             const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma,
+                             float* dbeta, float* partial_ws, int accumulate, int M, int D, float* gprompt, int T,
+                             int row0, int n_ctx, void* stream);
 int mfk_ln_bwd_ctas(int M);
 int mfk_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
                       const float* gamma, const float* g_in, float* g_out, void* g_out_bf16, float* dgamma,
@@ -120,6 +131,9 @@ int mfk_prompt_splice_fwd(float* x, const float* prompt, int N, int T, int row0,
  * rows are then cleared in g and g_bf16 (the spliced-away outputs of the previous layer get no gradient). */
 int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int N, int T, int row0, int n_ctx, int D,
                           int round_fp16, int zero_rows, void* stream);
+/* The same reduction for `layers` tensors at once (strides in elements): g + l*g_stride -> dprompt + l*dp_stride. */
+int mfk_prompt_splice_bwd_batched(float* g, long long g_stride, float* dprompt, long long dp_stride, int layers,
+                                  int N, int T, int row0, int n_ctx, int D, int round_fp16, void* stream);
 int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16, int R, int D, void* stream);
 /* scatter == 0: dst[r,:] = src[rowidx[r],:]; scatter != 0: dst[rowidx[r],:] = src[r,:] (dst pre-zeroed). Rows are
  * row_bytes long (multiple of 16). Only the CLS row (clip/model.py:567) / EOT row (trainers/maple.py:76) of the
