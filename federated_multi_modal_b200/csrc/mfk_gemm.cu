@@ -115,6 +115,28 @@ struct EpiCtx {
   int lane;
 };
 
+// Epilogue operands of one 32-row x 32-column chunk, fetched COALESCED: a lane that reads "its own row" touches 32
+// different 128-byte lines per load instruction (32 memory wavefronts each; the fp32-residual epilogue spent most
+// of its time there). Instead lane l loads, for j = 0..7, the float4 at (row 4j + l/8, columns 4(l%8)..) — 4 whole
+// rows per instruction — and finish_chunk transposes through the warp's staging buffer. Same idea for the bf16
+// QuickGELU aux (row 8j + l/4, 16-byte chunk l%4, j = 0..3).
+__device__ __forceinline__ void load_res_chunk(const GemmParams& p, int row0, int col, int lane, float4 (&rv)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = row0 + 4 * j + (lane >> 3);
+    rv[j] = r < p.M ? *reinterpret_cast<const float4*>(p.res + (size_t)r * p.ldres + col + 4 * (lane & 7))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void load_aux_chunk(const GemmParams& p, int row0, int col, int lane, uint4 (&av)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = row0 + 8 * j + (lane >> 2);
+    av[j] = r < p.M ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ldaux + col + 8 * (lane & 3)))
+                    : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // Epilogue math + stores of one 32-row x 32-column chunk held as v[32] (this lane's row): bias, QuickGELU
 // (+ pre-activation), * QuickGELU'(aux), + residual; outputs staged in swizzled smem and written by TMA.
 // row0 = first row of the 32-row group, col = first column, ok = this lane's element range is inside [M, N).
@@ -155,21 +177,50 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = quickgelu(__bfloat162float(__float2bfloat16_rn(v[j])));
   }
-  if (EPI == 2 && ok) {
+  const uint32_t sb = c.row128 - (uint32_t)c.lane * 128u;  // this warp's staging buffer
+  if constexpr (EPI == 2) {
+    // aux arrives as (row 8j + lane/4, 16-byte chunk lane%4): park it in the staging half this chunk will use for its
+    // output (64-byte rows, SWIZZLE_64B pattern), then every lane picks up its own row
+    const uint32_t ab = sb + poff;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 u0 = unpack_bf16(av[j].x), u1 = unpack_bf16(av[j].y), u2 = unpack_bf16(av[j].z),
-             u3 = unpack_bf16(av[j].w);
+      const uint32_t rr = 8u * j + ((uint32_t)c.lane >> 2);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ab + rr * 64u + ((((uint32_t)c.lane & 3u) ^ ((rr >> 1) & 3u)) << 4)),
+                   "r"(av[j].x), "r"(av[j].y), "r"(av[j].z), "r"(av[j].w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 a;
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                   : "r"(c.row64a + poff + ((j ^ c.x64) << 4)));
+      float2 u0 = unpack_bf16(a.x), u1 = unpack_bf16(a.y), u2 = unpack_bf16(a.z), u3 = unpack_bf16(a.w);
       v[8 * j] *= dquickgelu(u0.x); v[8 * j + 1] *= dquickgelu(u0.y);
       v[8 * j + 2] *= dquickgelu(u1.x); v[8 * j + 3] *= dquickgelu(u1.y);
       v[8 * j + 4] *= dquickgelu(u2.x); v[8 * j + 5] *= dquickgelu(u2.y);
       v[8 * j + 6] *= dquickgelu(u3.x); v[8 * j + 7] *= dquickgelu(u3.y);
     }
   }
-  if (EPI == 3 && ok) {
+  if constexpr (EPI == 3) {
+    // residual arrives as (row 4j + lane/8, 16-byte chunk lane%8): through the staging buffer (128-byte rows,
+    // SWIZZLE_128B pattern = the layout of the fp32 output image written below), then every lane adds its own row
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w;
+      const uint32_t rr = 4u * j + ((uint32_t)c.lane >> 3);
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sb + rr * 128u + ((((uint32_t)c.lane & 7u) ^ (rr & 7u)) << 4)),
+                   "f"(rv[j].x), "f"(rv[j].y), "f"(rv[j].z), "f"(rv[j].w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 x;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                   : "r"(c.row128 + ((j ^ c.x128) << 4)));
+      v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
     }
   }
   if (c.p.out16 || c.has_pre) {
@@ -315,16 +366,8 @@ __device__ __forceinline__ void splitk_unit(const EpiCtx& c, uint32_t taddr, int
         const bool ok = prow < p.M;
         float4 rv[EPI == 3 ? 8 : 1];
         uint4 av[EPI == 2 ? 4 : 1];
-        if (EPI == 3 && ok) {
-          const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)prow * p.ldres + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rv[j] = r4[j];
-        }
-        if (EPI == 2 && ok) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)prow * p.ldaux + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) av[j] = __ldg(a4 + j);
-        }
+        if constexpr (EPI == 3) load_res_chunk(p, m0 + rq * 32, col, lane, rv);
+        if constexpr (EPI == 2) load_aux_chunk(p, m0 + rq * 32, col, lane, av);
         finish_chunk<EPI>(c, v, rv, av, m0 + rq * 32, col, ok, pp++);
       }
       if (ew == 0 && lane == 0) GTRACE(2, 45);
@@ -539,18 +582,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (kSplitK && p.splitk && t >= p.full_tiles) return;  // split-K units fetch their operands in the fix-up pass
       int m0, n0, w;
       decode_tile(p, t, crank, m0, n0, w);
-      const int row = m0 + q * 32 + lane, col = n0 + c;
-      if (c >= w || row >= p.M || col >= p.N) return;
-      if (EPI == 3) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.res + (size_t)row * p.ldres + col);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rv_nx[j] = r4[j];
-      }
-      if (EPI == 2) {
-        const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) av_nx[j] = __ldg(a4 + j);
-      }
+      const int col = n0 + c;
+      if (c >= w || col >= p.N) return;
+      if constexpr (EPI == 3) load_res_chunk(p, m0 + q * 32, col, lane, rv_nx);
+      if constexpr (EPI == 2) load_aux_chunk(p, m0 + q * 32, col, lane, av_nx);
     };
     if (n_mine > 0) fetch_ops(tile_of(0), half * 32);
     uint32_t nchunk = 0;  // chunks finished by this warp (ping-pong parity of the staging buffer)
