@@ -238,7 +238,7 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
     if (trc) GTRACE(2, 59);
     if (c.lane == 0) {
       if (c.p.out16) tma_store_2d(c.tmO16, c.sbuf + poff, col, row0);
-      if (c.has_pre) tma_store_2d(c.tmPre, c.sbuf + 2048, col, row0);
+      if (c.has_pre) tma_store_2d_hint(c.tmPre, c.sbuf + 2048, col, row0, l2_policy_evict_first());
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
