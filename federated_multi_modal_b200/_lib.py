@@ -49,6 +49,8 @@ SIGNATURES = {
     "mfk_quickgelu_split_bf16x3": [P, P, I, I, P],
     "mfk_patch_im2col_f32": [P, P, I, I, P],
     "mfk_attn_fwd_f32": [P, P, I, I, I, I, P],
+    "mfk_attn_rows_fwd": [P, P, P, P, I, I, I, I, P],
+    "mfk_attn_rows_bwd": [P, P, P, P, P, I, I, I, I, P],
     "mfk_linear_small_fwd": [P, P, P, P, I, I, I, P],
     "mfk_linear_small_bwd": [P, P, P, P, P, P, P, I, I, I, P],
     "mfk_linear_small_fwd_grouped": [P, I, I, P],

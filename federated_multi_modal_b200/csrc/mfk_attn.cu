@@ -1554,3 +1554,168 @@ extern "C" int mfk_attn_fwd_f32(const float* qkv, float* out, int N, int T, int 
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
+
+// =====================================================================================================
+// Single-query attention for the LAST block of a tower: only one row per sequence (CLS / EOT) of the block output
+// is consumed (clip/model.py:567, trainers/maple.py:72-76), so the attention core is needed for that query row
+// only — Q of one row against K, V of the whole sequence — and so is its backward: dQ lives on that row, dK / dV are
+// rank-1 updates. One CTA per (head, sequence), 4 warps, fp32 arithmetic, fixed reduction orders (deterministic).
+//   forward : out_r[n, h*64..] = softmax(q_r K^T / 8 [causal: keys <= r]) V ;  lse_r[n, h] = log-sum-exp (natural)
+//   backward: dqkv[n*T + j] for every j: dV_j = p_j dO, dK_j = dS_j q_r / 8, dQ_j = 0 except row r: sum_j dS_j k_j / 8
+namespace {
+constexpr int ROWS_WARPS = 4;
+
+__device__ __forceinline__ float block_reduce_rows(float v, float* red, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < ROWS_WARPS; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// K and V slices (64 bf16 = 128 bytes per row) of this (sequence, head) -> shared memory, coalesced (8 lanes per row,
+// 16 rows per block-wide instruction, every load independent: one memory round trip instead of one per key)
+__device__ __forceinline__ void rows_stage_kv(const bf16* seq_base, int D3, int D, int T, uint4* sK, uint4* sV) {
+  for (int i = threadIdx.x; i < T * 8; i += blockDim.x) {
+    const int j = i >> 3, ch = i & 7;
+    sK[i] = __ldg(reinterpret_cast<const uint4*>(seq_base + (size_t)j * D3 + D) + ch);
+    sV[i] = __ldg(reinterpret_cast<const uint4*>(seq_base + (size_t)j * D3 + 2 * D) + ch);
+  }
+}
+// s[j] = scale * <vec, M_j> for j < kmax, M = staged [T][64] bf16; a warp takes keys w, w + 4, ... (2 dims per lane)
+__device__ __forceinline__ void rows_dots(const bf16* M, const float* vec, float* s, int kmax, float scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float v0 = vec[2 * lane], v1 = vec[2 * lane + 1];
+  for (int j = warp; j < kmax; j += ROWS_WARPS) {
+    const float2 k2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(M + (size_t)j * HD + 2 * lane));
+    const float d = warp_sum(v0 * k2.x + v1 * k2.y);
+    if (lane == 0) s[j] = d * scale;
+  }
+}
+// out[d] = sum_{j < kmax} w[j] * M_j[d]: thread t owns dim t & 63 and the keys of parity t >> 6; fixed-order combine
+__device__ __forceinline__ float rows_wsum(const bf16* M, const float* w, int kmax, float* comb) {
+  const int d = threadIdx.x & 63, part = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int j = part; j < kmax; j += 2) acc = fmaf(w[j], __bfloat162float(M[(size_t)j * HD + d]), acc);
+  __syncthreads();
+  comb[threadIdx.x] = acc;
+  __syncthreads();
+  return comb[d] + comb[64 + d];
+}
+
+__global__ void __launch_bounds__(ROWS_WARPS * 32)
+attn_rows_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ rows, bf16* __restrict__ out_r,
+                     float* __restrict__ lse_r, int T, int heads, int causal) {
+  extern __shared__ uint4 rows_smem[];
+  __shared__ float q[HD], s[256], red[ROWS_WARPS], comb[ROWS_WARPS * 32];
+  uint4* sK = rows_smem;
+  uint4* sV = rows_smem + (size_t)T * 8;
+  pdl_trigger();
+  pdl_wait();
+  const int h = blockIdx.x, n = blockIdx.y, D = heads * HD, D3 = 3 * D;
+  const int r = rows[n] - n * T;
+  const int kmax = causal ? r + 1 : T;
+  const bf16* seq = qkv + (size_t)n * T * D3 + h * HD;
+  rows_stage_kv(seq, D3, D, kmax, sK, sV);
+  if (threadIdx.x < HD) q[threadIdx.x] = __bfloat162float(seq[(size_t)r * D3 + threadIdx.x]);
+  __syncthreads();
+  rows_dots(reinterpret_cast<const bf16*>(sK), q, s, kmax, 0.125f);
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < kmax; j += blockDim.x) mx = fmaxf(mx, s[j]);
+  mx = block_reduce_rows(mx, red, true);
+  float l = 0.f;
+  for (int j = threadIdx.x; j < kmax; j += blockDim.x) {
+    const float e = expf(s[j] - mx);
+    s[j] = e;
+    l += e;
+  }
+  l = block_reduce_rows(l, red, false);
+  const float inv = 1.f / l;
+  for (int j = threadIdx.x; j < kmax; j += blockDim.x) s[j] *= inv;
+  __syncthreads();
+  const float o = rows_wsum(reinterpret_cast<const bf16*>(sV), s, kmax, comb);
+  if (threadIdx.x < HD) out_r[(size_t)n * D + h * HD + threadIdx.x] = __float2bfloat16_rn(o);
+  if (threadIdx.x == 0 && lse_r) lse_r[(size_t)n * heads + h] = mx + logf(l);
+}
+
+__global__ void __launch_bounds__(ROWS_WARPS * 32)
+attn_rows_bwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ rows, const bf16* __restrict__ d_out_r,
+                     const float* __restrict__ lse_r, bf16* __restrict__ dqkv, int T, int heads, int causal) {
+  extern __shared__ uint4 rows_smem[];
+  __shared__ float q[HD], da[HD], pr[256], ds[256], red[ROWS_WARPS], comb[ROWS_WARPS * 32];
+  uint4* sK = rows_smem;
+  uint4* sV = rows_smem + (size_t)T * 8;
+  pdl_trigger();
+  pdl_wait();
+  const int h = blockIdx.x, n = blockIdx.y, D = heads * HD, D3 = 3 * D;
+  const int r = rows[n] - n * T;
+  const int kmax = causal ? r + 1 : T;
+  const bf16* seq = qkv + (size_t)n * T * D3 + h * HD;
+  bf16* dseq = dqkv + (size_t)n * T * D3 + h * HD;
+  rows_stage_kv(seq, D3, D, kmax, sK, sV);
+  if (threadIdx.x < HD) {
+    q[threadIdx.x] = __bfloat162float(seq[(size_t)r * D3 + threadIdx.x]);
+    da[threadIdx.x] = __bfloat162float(d_out_r[(size_t)n * D + h * HD + threadIdx.x]);
+  }
+  __syncthreads();
+  rows_dots(reinterpret_cast<const bf16*>(sK), q, pr, kmax, 0.125f);   // scores
+  rows_dots(reinterpret_cast<const bf16*>(sV), da, ds, kmax, 1.0f);    // dP_j = <dO, v_j>
+  __syncthreads();
+  const float lse = lse_r[(size_t)n * heads + h];
+  float dl = 0.f;
+  for (int j = threadIdx.x; j < kmax; j += blockDim.x) {
+    const float p = expf(pr[j] - lse);
+    pr[j] = p;
+    dl += p * ds[j];
+  }
+  const float delta = block_reduce_rows(dl, red, false);
+  for (int j = threadIdx.x; j < kmax; j += blockDim.x) ds[j] = pr[j] * (ds[j] - delta);
+  __syncthreads();
+  const float dq = 0.125f * rows_wsum(reinterpret_cast<const bf16*>(sK), ds, kmax, comb);   // dQ_r[d]
+  __syncthreads();
+  if (threadIdx.x < HD) comb[threadIdx.x] = dq;
+  __syncthreads();
+  // every row of this (sequence, head): dQ (zero except row r), dK_j, dV_j — a warp per key, 2 dims per lane
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float q0 = q[2 * lane] * 0.125f, q1 = q[2 * lane + 1] * 0.125f, a0 = da[2 * lane], a1 = da[2 * lane + 1];
+  for (int j = warp; j < T; j += ROWS_WARPS) {
+    const float p = j < kmax ? pr[j] : 0.f, g = j < kmax ? ds[j] : 0.f;
+    bf16* row = dseq + (size_t)j * D3;
+    *reinterpret_cast<uint32_t*>(row + 2 * lane) = j == r ? pack_bf16(comb[2 * lane], comb[2 * lane + 1]) : 0u;
+    *reinterpret_cast<uint32_t*>(row + D + 2 * lane) = pack_bf16(g * q0, g * q1);
+    *reinterpret_cast<uint32_t*>(row + 2 * D + 2 * lane) = pack_bf16(p * a0, p * a1);
+  }
+}
+}  // namespace
+
+static int rows_smem_attr(const void* fn, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return e == cudaSuccess ? MFK_OK : (int)e;
+}
+
+extern "C" int mfk_attn_rows_fwd(const void* qkv, const int* rows, void* out_rows, float* lse_rows, int N, int T,
+                                 int heads, int causal, void* stream) {
+  if (!qkv || !rows || !out_rows || N <= 0 || T <= 0 || T > 256 || heads <= 0) return MFK_EARG;
+  const size_t smem = (size_t)T * 256;  // K and V slices of one (sequence, head)
+  if (int rc = rows_smem_attr(reinterpret_cast<const void*>(attn_rows_fwd_kernel), smem)) return rc;
+  launch_pdl(attn_rows_fwd_kernel, dim3(heads, N), dim3(ROWS_WARPS * 32), smem, static_cast<cudaStream_t>(stream),
+             static_cast<const bf16*>(qkv), rows, static_cast<bf16*>(out_rows), lse_rows, T, heads, causal);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_attn_rows_bwd(const void* qkv, const int* rows, const void* d_out_rows, const float* lse_rows,
+                                 void* dqkv, int N, int T, int heads, int causal, void* stream) {
+  if (!qkv || !rows || !d_out_rows || !lse_rows || !dqkv || N <= 0 || T <= 0 || T > 256 || heads <= 0) return MFK_EARG;
+  const size_t smem = (size_t)T * 256;
+  if (int rc = rows_smem_attr(reinterpret_cast<const void*>(attn_rows_bwd_kernel), smem)) return rc;
+  launch_pdl(attn_rows_bwd_kernel, dim3(heads, N), dim3(ROWS_WARPS * 32), smem, static_cast<cudaStream_t>(stream),
+             static_cast<const bf16*>(qkv), rows, static_cast<const bf16*>(d_out_rows), lse_rows,
+             static_cast<bf16*>(dqkv), T, heads, causal);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}

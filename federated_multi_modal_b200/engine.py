@@ -245,6 +245,7 @@ class MapleEngine:
         if train:
             ws["u_r"] = b("u_r", (R, 4 * D), BF16)
             ws["stat_r"] = b("stat_r", (2, R), F32)
+            ws["lse_r"] = b("lse_r", (R * tw.heads,), F32)
             ws["g_r"] = b("g_r", (R, D), F32)
             ws["g16_r"] = b("g16_r", (R, D), BF16)
             ws["du_r"] = b("du_r", (R, 4 * D), BF16)
@@ -324,10 +325,10 @@ class MapleEngine:
         ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_bf16=ws["h"], mean=st[0], rstd=st[1], splice=splice)
         qkv, att = ws["qkv"][s], ws["att"][s]
         ops.gemm(ws["h"], w["attn.in_proj.w"], bias=w["attn.in_proj.b"], out_bf16=qkv, ws=tw.gemm_ws)
-        ops.attn_fwd(qkv, att, ws["lse"][l] if train else None, tw.N, tw.T, tw.heads, tw.causal)
         if rows is not None:
+            # last block: the attention core is needed for the consumed (CLS / EOT) query row of each sequence only
             sr = ws["stat_r"] if train else (None, None)
-            ops.gather_rows(att, rows, ws["att_r"])
+            ops.attn_rows_fwd(qkv, rows, ws["att_r"], ws["lse_r"] if train else None, tw.N, tw.T, tw.heads, tw.causal)
             ops.gather_rows(x1, rows, ws["x1_r"])
             ops.gemm(ws["att_r"], w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=ws["x1_r"],
                      out_f32=ws["x2_r"])
@@ -337,6 +338,8 @@ class MapleEngine:
             ops.gemm(ws["act_r"], w["mlp.c_proj.w"], bias=w["mlp.c_proj.b"], residual=ws["x2_r"],
                      out_f32=ws["xout_r"])
             return ws["xout_r"]
+        ops.attn_fwd(qkv, att, ws["lse"][l], tw.N, tw.T, tw.heads, tw.causal) if train else \
+            ops.attn_fwd(qkv, att, None, tw.N, tw.T, tw.heads, tw.causal)
         ops.gemm(att, w["attn.out_proj.w"], bias=w["attn.out_proj.b"], residual=x1, out_f32=x2, ws=tw.gemm_ws)
         ops.layernorm_fwd(x2, w["ln_2.g"], w["ln_2.b"], y_bf16=ws["h2"], mean=st[2], rstd=st[3])
         ops.gemm(ws["h2"], w["mlp.c_fc.w"], bias=w["mlp.c_fc.b"], act=1, out_bf16=ws["act"],
@@ -386,7 +389,7 @@ class MapleEngine:
     def _last_block_bwd_rows(self, tw: _Tower, rows):
         """Backward of the last block's out-proj + MLP on the gathered rows. In: ws["g_r"] / ws["g16_r"] = gradient
         at the block output rows. Out: ws["g"] / ws["g16"] (full, zero except `rows`) = gradient after the attention
-        residual, ws["dh"] (full bf16, zero except `rows`) = gradient wrt the attention output."""
+        residual, ws["dh_r"] (compact bf16 [R, D]) = gradient wrt the attention output rows."""
         l = tw.L - 1
         ws, w, D = tw.ws, tw.w[l], tw.D
         pre = f"{tw.name}.transformer.resblocks.{l}."
@@ -408,9 +411,9 @@ class MapleEngine:
         if wg:
             ops.gemm_at_b(g16, ws["att_r"], G[pre + "attn.out_proj.weight"])
             ops.colsum(g, G[pre + "attn.out_proj.bias"], ws["csum"])
-        ws["g"].zero_(); ws["g16"].zero_(); ws["dh"].zero_()
+        ws["g"].zero_(); ws["g16"].zero_()
         ops.scatter_rows(g, rows, ws["g"], ws["g16"])
-        ops.gather_rows(ws["dh_r"], rows, ws["dh"], scatter=True)
+        tw.last_rows = rows  # ws["dh_r"] (gradient wrt the attention output rows) feeds the single-query backward
 
     def _block_bwd(self, tw: _Tower, l: int, attn_only: bool = False, splice_grad=None):
         """attn_only: the MLP / out-proj part was already done on gathered rows (_last_block_bwd_rows)."""
@@ -422,9 +425,8 @@ class MapleEngine:
         ln_grads = self.trainable == "reference"
         G = self.g
         if attn_only:
-            da = ws["dh"]
-            ops.attn_bwd(ws["qkv"][l], ws["att"][l], da, ws["lse"][l], ws["delta"], ws["dqkv"], tw.N, tw.T, tw.heads,
-                         tw.causal)
+            ops.attn_rows_bwd(ws["qkv"][l], tw.last_rows, ws["dh_r"], ws["lse_r"], ws["dqkv"], tw.N, tw.T, tw.heads,
+                              tw.causal)
             ops.gemm(ws["dqkv"], w["attn.in_proj.wT"], out_bf16=ws["dh"], ws=tw.gemm_ws)
             if wg:
                 self._wgrad(tw, ws["dqkv"], ws["h"], G[pre + "attn.in_proj_weight"], 3 * D, D)

@@ -190,6 +190,17 @@ def patch_im2col_f32(img, out):
     call("mfk_patch_im2col_f32", img, out, img.shape[0], img.shape[-1], stream_ptr())
 
 
+def attn_rows_fwd(qkv, rows, out_rows, lse_rows, N, T, heads, causal):
+    """Attention core for ONE query row per sequence (rows int32 [N], global row indices): the last block's CLS/EOT."""
+    _chk(qkv, BF16, "qkv"); _chk(out_rows, BF16, "out_rows")
+    call("mfk_attn_rows_fwd", qkv, rows, out_rows, lse_rows, N, T, heads, int(causal), stream_ptr())
+
+
+def attn_rows_bwd(qkv, rows, d_out_rows, lse_rows, dqkv, N, T, heads, causal):
+    _chk(qkv, BF16, "qkv"); _chk(d_out_rows, BF16, "d_out_rows"); _chk(dqkv, BF16, "dqkv")
+    call("mfk_attn_rows_bwd", qkv, rows, d_out_rows, lse_rows, dqkv, N, T, heads, int(causal), stream_ptr())
+
+
 def attn_fwd_f32(qkv, out, N, T, heads, causal):
     _chk(qkv, F32, "qkv"); _chk(out, F32, "out")
     call("mfk_attn_fwd_f32", qkv, out, N, T, heads, int(causal), stream_ptr())

@@ -149,6 +149,14 @@ int mfk_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
  * B operand is packed [hi | hi | lo]; one mfk_gemm_bf16 of depth 3D then carries ~16 mantissa bits. Used for the
  * feature heads (`x @ proj`, clip/model.py:569-570; `@ text_projection`, trainers/maple.py:76).        */
 int mfk_split_bf16x3(const float* x, void* out_bf16, int rows, int D, void* stream);
+/* Single-query attention for the LAST block of a tower: only the CLS / EOT row of each sequence is consumed after
+ * it (clip/model.py:567; trainers/maple.py:72-76), so the core runs for that query row alone. rows[n] = global row
+ * (n*T + position) of the consumed row; out_rows / d_out_rows bf16 [N, D]; lse_rows fp32 [N, heads].
+ * Backward fills ALL rows of dqkv for the N sequences: dQ is zero except the consumed row.                       */
+int mfk_attn_rows_fwd(const void* qkv, const int* rows, void* out_rows, float* lse_rows, int N, int T, int heads,
+                      int causal, void* stream);
+int mfk_attn_rows_bwd(const void* qkv, const int* rows, const void* d_out_rows, const float* lse_rows, void* dqkv,
+                      int N, int T, int heads, int causal, void* stream);
 /* fp32 mode (parity contract: logits within 1e-3 of the reference's fp32 path; inference only). Every GEMM runs
  * on the same tcgen05 kernel with hi|lo|hi x hi|hi|lo split operands (K -> 3K, fp32 out); these are the pieces in
  * between: exact-sigmoid QuickGELU + split (clip/model.py:162-164), fp32 im2col (clip/model.py:514) and an fp32

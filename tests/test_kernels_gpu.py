@@ -174,6 +174,30 @@ def test_attention_fwd_bwd(N, T, heads, causal, impl):
     assert err < 3e-2 * max(1.0, x.grad.abs().max().item()), err
 
 
+@pytest.mark.parametrize("N,T,heads,causal", [(4, 199, 12, False), (6, 10, 8, True), (3, 77, 8, True)])
+def test_attention_single_query_rows(N, T, heads, causal):
+    """Last-block attention for one consumed row per sequence == the dense attention restricted to that row, forward
+    and backward (dQ only on the row, rank-1 dK / dV)."""
+    D = heads * 64
+    qkv = rnd(N * T, 3 * D, dtype=BF16, seed=12)
+    pos = torch.tensor([(3 * i + 1) % T for i in range(N)]) if causal else torch.zeros(N, dtype=torch.long)
+    rows = (torch.arange(N) * T + pos).to(DEV, torch.int32)
+    out_r = torch.empty(N, D, device=DEV, dtype=BF16)
+    lse_r = torch.empty(N * heads, device=DEV, dtype=F32)
+    ops.attn_rows_fwd(qkv, rows, out_r, lse_r, N, T, heads, causal)
+    x = qkv.float().requires_grad_(True)
+    o_ref, _, _ = _attn_ref(x, N, T, heads, causal)
+    o_rows = o_ref[rows.long()]
+    assert (out_r.float() - o_rows).abs().max().item() < 2e-2
+    d_out_r = rnd(N, D, dtype=BF16, seed=13)
+    o_rows.backward(d_out_r.float())
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attn_rows_bwd(qkv, rows, d_out_r, lse_r, dqkv, N, T, heads, causal)
+    assert torch.isfinite(dqkv.float()).all()
+    err = (dqkv.float() - x.grad).abs().max().item()
+    assert err < 3e-2 * max(1.0, x.grad.abs().max().item()), err
+
+
 @pytest.mark.parametrize("N,T,heads,causal", [(3, 199, 12, False), (5, 10, 8, True), (2, 77, 8, True)])
 def test_attention_fp32_mode(N, T, heads, causal):
     D = heads * 64
