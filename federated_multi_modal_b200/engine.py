@@ -780,10 +780,12 @@ class MapleEngine:
         def tower(D, L, T, N, causal, wg):
             lin = 2 * N * T * D * (3 * D + D + 4 * D + 4 * D)            # one full layer, forward
             att = 4 * N * T * T * D * ((T + 1) / (2 * T) if causal else 1.0)
-            # last layer: in-proj + attention on all rows, out-proj + MLP only on the N consumed rows
+            # last layer: in-proj on all rows; attention for the ONE consumed query row of each sequence (att / T);
+            # out-proj + MLP only on the N consumed rows
             last = 2 * N * T * D * 3 * D + 2 * N * D * (D + 4 * D + 4 * D)
-            fwd = (L - 1) * (lin + att) + last + att
-            bwd = (L - 1) * (lin + 2 * att) + last + 2 * att + (last if wg else 0)
+            att1 = att / T
+            fwd = (L - 1) * (lin + att) + last + att1
+            bwd = (L - 1) * (lin + 2 * att) + last + 2 * att1 + (last if wg else 0)
             return fwd, bwd
         vf, vb = tower(self.vis.D, self.vis.L, self.Tv, B, False, self.wgrad_last)
         tf, tb = tower(self.txt.D, self.txt.L, self.Te, self.C, True, self.wgrad_last)
