@@ -272,9 +272,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: everything else any library prints (NCCL's version banner appears on
+    # stdout at communicator creation) is sent to stderr; the JSON goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     trainer = make_trainer(dev, graph=not args.no_graph)
     eng = trainer.model.engine
@@ -394,7 +398,9 @@ def run_ours(args):
                                          sorted(prof.items(), key=lambda kv: -kv[1]["s_per_step"])},
             "loss": loss_now,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
