@@ -1098,6 +1098,10 @@ extern "C" int mfk_attn_bwd_tc(const void* qkv, const void* out, const void* d_o
 namespace {
 using namespace mfk;
 
+// 8 compute warps + two single-thread MMA issuers: tcgen05.mma issue costs ~70 cycles per instruction from one
+// thread, and a block needs 32 of them, so S/dP + dQ and dV + dK are issued from two warps in parallel.
+constexpr int FUSED_THREADS = (TC_SOFTMAX_WARPS + 2) * 32;
+
 struct AttnBwdFusedParams {
   const float* lse;
   const bf16* out;    // forward output O  [rows, D]
@@ -1113,7 +1117,7 @@ struct AttnBwdFusedParams {
     if (p.trace && blockIdx.x == 0 && trc_n < 60) p.trace[(slot) * 64 + trc_n++] = clock64(); \
   } while (0)
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
 attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmDo,
                          const AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw_f[];
@@ -1148,7 +1152,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       mbar_init(ld_full, 1);
       mbar_init(sd_full, 1);
       mbar_init(ds_full, TC_SOFTMAX_WARPS);
-      mbar_init(mma2_done, 1);
+      mbar_init(mma2_done, 2);  // one commit per issuing thread
       mbar_init(dkv_free, TC_SOFTMAX_WARPS);
       mbar_init(unit_free, TC_SOFTMAX_WARPS);
       fence_barrier_init();
@@ -1165,8 +1169,9 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   pdl_trigger();
   pdl_wait();
 
-  if (warp == TC_SOFTMAX_WARPS) {
+  if (warp >= TC_SOFTMAX_WARPS) {
     if (lane == 0) {
+      const bool issuer_a = warp == TC_SOFTMAX_WARPS;  // A: TMA loads, S / dP, dQ.   B: dV, dK.
       uint32_t blk_ctr = 0, kt_ctr = 0;
       const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_tt = umma_idesc_bf16(128, HD, 1, 1);  // A, B MN-major (dV, dK)
@@ -1188,6 +1193,10 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + colDP, ad + 2ull * k, bv + 2ull * k, idesc1, k > 0);
         umma_commit(sd_full);
       };
+      // reduction depth in 16-row steps: the last query / key tile holds only T - 128 (NT - 1) valid rows (its staged
+      // rows / columns beyond T are zero), so the MMAs over the all-zero tail are not issued. Plain runtime loops:
+      // `#pragma unroll` + `if (ks < n)` around the tcgen05.mma asm miscompiled (nvcc 12.9: illegal address at run
+      // time even with the predicate always true).
       const int ks_last = (p.T - (NT - 1) * 128 + 15) / 16;
       int trc_n = 0;
       auto issue_loads = [&](int u) {
@@ -1200,56 +1209,63 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         tma_load_2d(&tmQkv, ld_full, sV, 2 * D + h * HD, row0);
         tma_load_2d(&tmDo, ld_full, sdO, h * HD, row0);
       };
-      if (n_units > 0) issue_loads(0);
-      for (int u = 0; u < n_units; ++u) {
-        // the TMEM accumulators of the previous unit must be drained; its loads were issued early (below)
-        mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
-        TRC(0);  // unit start (previous unit drained)
-        mbar_wait(ld_full, (uint32_t)u & 1u);
-        TRC(0);  // loads landed
-        tc_fence_after();
-        issue_sdp(0, 0);
-        TRC(0);  // S/dP issued
-        for (int k = 0; k < nblk; ++k, ++blk_ctr) {
-          const int j = k / NT, i = k % NT;
-          mbar_wait(ds_full, blk_ctr & 1u);
-          TRC(0);  // staged operands ready
-          // S/dP of the NEXT block go first: the compute warps have finished reading the S/dP columns, and their
-          // exp / dS arithmetic for block k + 1 then overlaps the second-stage MMAs of block k (they wait for
-          // mma2_done before overwriting the staged P / dS tiles those MMAs read).
+      if (issuer_a) {
+        if (n_units > 0) issue_loads(0);
+        for (int u = 0; u < n_units; ++u) {
+          // the TMEM accumulators of the previous unit must be drained; its loads were issued early (below)
+          mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
+          TRC(0);  // unit start (previous unit drained)
+          mbar_wait(ld_full, (uint32_t)u & 1u);
+          TRC(0);  // loads landed
           tc_fence_after();
-          if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
-          if (i == 0 && j > 0) {  // accumulators of the previous key tile must have been drained
-            mbar_wait(dkv_free, kt_ctr & 1u);
-            ++kt_ctr;
+          issue_sdp(0, 0);
+          TRC(0);  // S/dP issued
+          for (int k = 0; k < nblk; ++k, ++blk_ctr) {
+            const int j = k / NT, i = k % NT;
+            mbar_wait(ds_full, blk_ctr & 1u);
+            TRC(0);  // staged operands ready
+            // S/dP of the NEXT block go first: the compute warps have finished reading the S/dP columns, and their
+            // exp / dS arithmetic for block k + 1 then overlaps the second-stage MMAs of block k (they wait for
+            // mma2_done before overwriting the staged P / dS tiles those MMAs read).
             tc_fence_after();
+            if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
+            const uint64_t bk = dKm + 1024ull * j;
+            const uint32_t acc_j = j > 0;
+            const int ks_j = j == NT - 1 ? ks_last : 8;
+            for (int ks = 0; ks < ks_j; ++ks)  // dQ_i += dS K_j        (K = keys of tile j: 2 column blocks x 4 k-steps)
+              umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, dDsk + 1024ull * (ks >> 2) + 2ull * (ks & 3),
+                        bk + 128ull * ks, idesc_kt, acc_j | (ks > 0));
+            umma_commit(mma2_done);
+            TRC(0);  // second-stage (+ next S/dP) issued
           }
-          {
-            const uint64_t bdo = dDom + 1024ull * i, bq = dQm + 1024ull * i, bk = dKm + 1024ull * j;
-            const uint32_t acc_i = i > 0, acc_j = j > 0;
-            // reduction depth in 16-row steps: the last query / key tile holds only T - 128 (NT - 1) valid rows
-            // (its staged rows / columns beyond T are zero), so the MMAs over the all-zero tail are not issued.
-            // Plain runtime loops: `#pragma unroll` + `if (ks < n)` around the tcgen05.mma asm miscompiled (nvcc 12.9:
-            // illegal address at run time even with the predicate always true).
-            const int ks_i = i == NT - 1 ? ks_last : 8, ks_j = j == NT - 1 ? ks_last : 8;
+          // Q, K, V, dO are free once the last block's MMAs (of both issuers) have retired: the next unit's loads run
+          // under this unit's epilogue (the compute warps read TMEM and lse / O / dO from global memory)
+          mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
+          if (u + 1 < n_units) issue_loads(u + 1);
+        }
+      } else {
+        for (int u = 0; u < n_units; ++u) {
+          for (int k = 0; k < nblk; ++k, ++blk_ctr) {
+            const int j = k / NT, i = k % NT;
+            mbar_wait(ds_full, blk_ctr & 1u);
+            if (i == 0 && j > 0) {  // accumulators of the previous key tile must have been drained
+              mbar_wait(dkv_free, kt_ctr & 1u);
+              ++kt_ctr;
+            }
+            tc_fence_after();
+            const uint64_t bdo = dDom + 1024ull * i, bq = dQm + 1024ull * i;
+            const uint32_t acc_i = i > 0;
+            const int ks_i = i == NT - 1 ? ks_last : 8;
             for (int ks = 0; ks < ks_i; ++ks)  // dV_j += P^T dO_i   (K = query rows of tile i, 16 per MMA)
               umma_bf16(tmem_base + colDV, dPm + 128ull * ks, bdo + 128ull * ks, idesc_tt, acc_i | (ks > 0));
             for (int ks = 0; ks < ks_i; ++ks)  // dK_j += dS^T Q_i
               umma_bf16(tmem_base + colDK, dDsm + 128ull * ks, bq + 128ull * ks, idesc_tt, acc_i | (ks > 0));
-            for (int ks = 0; ks < ks_j; ++ks)  // dQ_i += dS K_j        (K = keys of tile j: 2 column blocks x 4 k-steps)
-              umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, dDsk + 1024ull * (ks >> 2) + 2ull * (ks & 3),
-                        bk + 128ull * ks, idesc_kt, acc_j | (ks > 0));
+            umma_commit(mma2_done);
           }
-          umma_commit(mma2_done);
-          TRC(0);  // second-stage (+ next S/dP) issued
+          // the last key tile's dkv_free arrive is consumed here so the phase counters stay in step
+          mbar_wait(dkv_free, kt_ctr & 1u);
+          ++kt_ctr;
         }
-        // Q, K, V, dO are free once the last block's MMAs have retired: the next unit's loads run under this unit's
-        // epilogue (the compute warps read their accumulators from TMEM and lse / O / dO from global memory)
-        mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
-        if (u + 1 < n_units) issue_loads(u + 1);
-        // the last key tile's dkv_free arrive is consumed here so the phase counters stay in step
-        mbar_wait(dkv_free, kt_ctr & 1u);
-        ++kt_ctr;
       }
     }
     __syncwarp();
@@ -1463,7 +1479,7 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   e = cudaFuncSetAttribute(attn_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.total_units < g_attn_sms ? p.total_units : g_attn_sms;
-  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmQkv, tmDo, p);
+  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(FUSED_THREADS), smem, st, tmQkv, tmDo, p);
   if (e != cudaSuccess) return (int)e;
   return MFK_OK;
 }
