@@ -143,12 +143,14 @@ __device__ __forceinline__ void load_aux_chunk(const GemmParams& p, int row0, in
 template <int EPI>
 __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], const float4 (&rv)[EPI == 3 ? 8 : 1],
                                              const uint4 (&av)[EPI == 2 ? 4 : 1], int row0, int col, bool ok,
-                                             uint32_t pp) {
+                                             uint32_t pp, const float4* bpre = nullptr) {
   if (EPI != 2 && c.p.bias && col < c.p.N) {
+    // bpre: the chunk's 32 bias values, fetched by the caller ahead of the TMEM load (their L2 latency then hides
+    // behind it instead of following it)
     const float4* b4 = reinterpret_cast<const float4*>(c.p.bias + col);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 bv = __ldg(b4 + j);
+      const float4 bv = bpre ? bpre[j] : __ldg(b4 + j);
       v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
     }
   }
@@ -156,26 +158,34 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
   // (pp = chunk parity) and only the store before the previous one must have finished READING its half, so the TMA
   // store of chunk i overlaps the arithmetic of chunk i + 1. Otherwise the whole buffer is reused every chunk.
   const GemmParams& p = c.p;
-  const bool trc = (threadIdx.x == 128);  // warp 4 lane 0
-  if (trc) GTRACE(2, 56);
+  const bool trc = (threadIdx.x == 128) && pp == 4;  // warp 4 lane 0, first chunk of its second tile
+  if (trc) GTRACE(2, 32);
   const bool pingpong = EPI != 1 && EPI != 3 && c.p.out16 && !c.p.out32;
   const uint32_t poff = pingpong ? (pp & 1u) * 2048u : 0u;
   if (pingpong) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
   else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
-  if (trc) GTRACE(2, 57);
+  if (trc) GTRACE(2, 33);
   if (EPI == 1) {
+    // bf16-round the pre-activation ONCE with the packed (ALU-pipe) conversion: the same words are stored as the
+    // saved pre-activation and unpacked by shifts as the activation's input. The scalar round trip
+    // (F2F.BF16.F32 per element) runs on the quarter-rate XU pipe that the 32 tanh of the chunk already saturate.
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
     if (c.has_pre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.row64b + ((j ^ c.x64) << 4)),
-                     "r"(pack_bf16(v[8 * j], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
-                     "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.row64b + ((j ^ c.x64) << 4)), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                      : "memory");
     }
     // the activation is applied to the bf16-rounded pre-activation that backward will re-read
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = quickgelu(__bfloat162float(__float2bfloat16_rn(v[j])));
+    for (int j = 0; j < 16; ++j) {
+      v[2 * j] = quickgelu(__uint_as_float(pk[j] << 16));
+      v[2 * j + 1] = quickgelu(__uint_as_float(pk[j] & 0xffff0000u));
+    }
   }
   const uint32_t sb = c.row128 - (uint32_t)c.lane * 128u;  // this warp's staging buffer
   if constexpr (EPI == 2) {
@@ -232,15 +242,21 @@ __device__ __forceinline__ void finish_chunk(const EpiCtx& c, float (&v)[32], co
                      "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
                      : "memory");
     }
-    if (trc) GTRACE(2, 58);
+    if (trc) GTRACE(2, 34);
     fence_proxy_async();
     __syncwarp();
-    if (trc) GTRACE(2, 59);
-    if (c.lane == 0) {
-      if (c.p.out16) tma_store_2d(c.tmO16, c.sbuf + poff, col, row0);
-      if (c.has_pre) tma_store_2d_hint(c.tmPre, c.sbuf + 2048, col, row0, l2_policy_evict_first());
+    if (trc) GTRACE(2, 35);
+    // the two stores are issued (and their bulk groups tracked) by two different lanes: one lane takes ~200 cycles
+    // per UTMASTG + commit, and every lane executes the wait_group above before the staging buffer is reused
+    if (c.lane == 0 && c.p.out16) {
+      tma_store_2d(c.tmO16, c.sbuf + poff, col, row0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    if (c.lane == 1 && c.has_pre) {
+      tma_store_2d_hint(c.tmPre, c.sbuf + 2048, col, row0, l2_policy_evict_first());
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (trc) GTRACE(2, 36);
   }
   if (c.p.out32) {
     if (c.p.out16 || c.has_pre) {  // the fp32 image needs the whole buffer: wait for the bf16 stores to drain it
@@ -634,6 +650,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (warp == 4 && lane == 0) GTRACE(2, 2 * it);
         }
         if (it == 1 && warp == 4 && lane == 0) GTRACE(2, 48 + 3 * (c >> 6));
+        float4 bv[8];
+        if (EPI != 2 && p.bias && col < p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+        }
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tc_wait_ld();
@@ -641,7 +662,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        finish_chunk<EPI>(ctx, v, rv, av, m0 + q * 32, col, ok, nchunk++);
+        finish_chunk<EPI>(ctx, v, rv, av, m0 + q * 32, col, ok, nchunk++, bv);
         if (it == 1 && warp == 4 && lane == 0) GTRACE(2, 50 + 3 * (c >> 6));
       }
       if (!waited) {  // narrow tile: this warp had no chunk, but it still takes part in the hand-shake

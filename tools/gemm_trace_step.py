@@ -77,6 +77,13 @@ for i, N, K, act, has_res, buf in bufs:
         if int(ep[40]) > 0:
             print("  CTA%3d split-K unit: partial written @%d | fenced+barrier @%d | all slices seen @%d | slices summed @%d | "
                   "combined @%d | finished @%d | re-armed @%d" % ((cta,) + tuple(rel(ep[i]) for i in range(40, 47))))
+        if int(ep[48]) > 0:  # chunk-level stamps of warp 4 in its second tile: (before tmem ld, after ld, chunk done) x 4
+            print("  CTA%3d tile1 chunks: " % cta + " | ".join(
+                "ld @%d +%d fin +%d" % (rel(ep[48 + 3 * j]), int(ep[49 + 3 * j] - ep[48 + 3 * j]), int(ep[50 + 3 * j] - ep[49 + 3 * j]))
+                for j in range(4) if int(ep[48 + 3 * j]) > 0))
+            if int(ep[32]) > 0:
+                print("  CTA%3d tile1 chunk0 inside finish_chunk: entry @%d | staging free +%d | math+st.shared +%d | fence+syncwarp +%d | stores issued +%d"
+                      % (cta, rel(ep[32]), int(ep[33] - ep[32]), int(ep[34] - ep[33]), int(ep[35] - ep[34]), int(ep[36] - ep[35])))
         print(f"  CTA{cta:3d} stores drained @{rel(ep[62])}")
     res.append(dict(i=i, N=N, K=K, act=act, res=has_res, wait=float(wait.mean()), busy_mean=float((end - wait).mean()),
                     busy_max=float((end - wait).max())))
