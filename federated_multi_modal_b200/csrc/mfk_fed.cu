@@ -93,9 +93,24 @@ fedavg_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ we
 }
 
 template <typename TIN>
-__global__ void check_finite_kernel(const TIN* __restrict__ p, long long n, int* __restrict__ flag) {
+__global__ void check_finite_kernel(const TIN* __restrict__ p, long long n, int* __restrict__ flag, bool vec) {
   bool bn = false, bi = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  // 16-byte loads over the aligned body (the C ABI requires a 16-byte aligned base), scalar tail
+  constexpr int V = 16 / (int)sizeof(TIN);
+  const long long nv = vec ? n / V : 0;  // base not 16-byte aligned: all scalar
+  const uint4* p4 = reinterpret_cast<const uint4*>(p);
+  for (long long i = tid; i < nv; i += nthr) {
+    const uint4 u = p4[i];
+    const TIN* e = reinterpret_cast<const TIN*>(&u);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float v = (float)e[j];
+      bn |= isnan(v);
+      bi |= isinf(v);
+    }
+  }
+  for (long long i = nv * V + tid; i < n; i += nthr) {
     const float v = (float)p[i];
     bn |= isnan(v);
     bi |= isinf(v);
@@ -186,11 +201,11 @@ extern "C" int mfk_fedavg_reduce(const void* const* client_ptrs_dev, const float
 
 extern "C" int mfk_check_finite(const void* p, long long n, int dtype, int* flag_dev, void* stream) {
   if (!p || n <= 0 || !flag_dev) return MFK_EARG;
-  long long blocks = (n + 1023) / 1024;
+  long long blocks = (n + 4095) / 4096;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (dtype == 0) check_finite_kernel<float><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const float*>(p), n, flag_dev);
-  else if (dtype == 1) check_finite_kernel<__half><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const __half*>(p), n, flag_dev);
-  else if (dtype == 2) check_finite_kernel<bf16><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(p), n, flag_dev);
+  if (dtype == 0) check_finite_kernel<float><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const float*>(p), n, flag_dev, mfk_aligned16(p));
+  else if (dtype == 1) check_finite_kernel<__half><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const __half*>(p), n, flag_dev, mfk_aligned16(p));
+  else if (dtype == 2) check_finite_kernel<bf16><<<(unsigned)blocks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(p), n, flag_dev, mfk_aligned16(p));
   else return MFK_EARG;
   MFK_CHECK_LAUNCH();
   return MFK_OK;

@@ -57,12 +57,13 @@ class FedAvgExchange:
             self.send = torch.zeros(k_local, n, device=self.dev, dtype=torch.float32)
         self.gathered = None if self._symm is not None else torch.zeros(self.K, n, device=self.dev,
                                                                          dtype=torch.float32)
-        self.status_local = torch.zeros(k_local, 2, device=self.dev, dtype=torch.float32)  # [ok, n_samples]
-        self.status = torch.zeros(self.K, 2, device=self.dev, dtype=torch.float32)
+        # per client: [ok, n_samples, NaN/Inf flag word of its published tensor (1 = NaN, 2 = Inf)]
+        self.status_local = torch.zeros(k_local, 3, device=self.dev, dtype=torch.float32)
+        self.status = torch.zeros(self.K, 3, device=self.dev, dtype=torch.float32)
+        self.flags_local = torch.zeros(k_local, device=self.dev, dtype=torch.int32)
         if cuda:
             self.out32 = torch.zeros(n, device=self.dev, dtype=torch.float32)
             self.out16 = torch.zeros(n, device=self.dev, dtype=torch.float16)
-            self.flags = torch.zeros(self.K, device=self.dev, dtype=torch.int32)
 
     # -------------------------------------------------------------------- stage 1: publish + gather
     def publish(self, j: int, arena: torch.Tensor, ok: bool = True, n_samples: float = 1.0):
@@ -70,8 +71,22 @@ class FedAvgExchange:
         self.status_local[j, 0] = 1.0 if ok else 0.0
         self.status_local[j, 1] = float(n_samples)
 
+    def _scan_local(self):
+        """check_weights_valid (trainers/maple_fed.py:317-325) of this rank's OWN clients, on the device and out of
+        local HBM; the flag words travel with the status all-gather, so no rank ever scans a peer's tensor."""
+        self.flags_local.zero_()
+        if self.dev.type == "cuda":
+            from . import ops
+            for j in range(self.k_local):
+                ops.check_finite(self.send[j], self.flags_local[j:j + 1])
+        else:  # host logic under the gloo tests
+            for j in range(self.k_local):
+                self.flags_local[j] = int(torch.isnan(self.send[j]).any()) | (int(torch.isinf(self.send[j]).any()) << 1)
+        self.status_local[:, 2] = self.flags_local.to(torch.float32)
+
     def gather(self) -> List[torch.Tensor]:
         """Returns the K client rows in client order (views; peer memory for the p2p transport)."""
+        self._scan_local()
         if self.world == 1:
             self.status.copy_(self.status_local)
             return [self.send[j] for j in range(self.k_local)]
@@ -92,14 +107,8 @@ class FedAvgExchange:
         (failed locally, or NaN/Inf in their tensors — check_weights_valid, trainers/maple_fed.py:271-277)
         are excluded; the divisor is the number (or sample count) of the valid ones."""
         from . import ops
-        status = self.status.cpu()
-        # validity scan of every client's tensor (device side, one flag word per client)
-        self.flags.zero_()
-        for k, r in enumerate(rows):
-            ops.check_finite(r, self.flags[k:k + 1])
-        if self._symm is not None:
-            pass
-        bad = self.flags.cpu()
+        status = self.status.cpu()  # the one host synchronisation of the exchange
+        bad = status[:, 2].to(torch.int32)  # validity scans ran on the owners' GPUs (gather)
         valid = [k for k in range(self.K) if status[k, 0] > 0 and int(bad[k]) == 0]
         if not valid:
             return None, None, valid, bad
