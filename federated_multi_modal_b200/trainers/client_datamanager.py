@@ -49,11 +49,25 @@ class _Loader:
                        "impath": [self.items[i].impath for i in idx]}
                 continue
             imgs = [self.items[i].img if self.tfm is None else self.tfm(self.items[i]) for i in idx]
-            img = torch.stack(imgs)
             lab = torch.tensor([self.items[i].label for i in idx], dtype=torch.long)
             if torch.cuda.is_available():
-                img, lab = img.pin_memory(), lab.pin_memory()
+                img = torch.stack(imgs, out=self._staging(b, len(imgs), imgs[0]))  # straight into pinned memory
+                lab = lab.pin_memory()
+            else:
+                img = torch.stack(imgs)
             yield {"img": img, "label": lab, "impath": [self.items[i].impath for i in idx]}
+
+    _SLOTS = 3  # batches alive at once: one in flight on the GPU, one being assembled, one spare
+
+    def _staging(self, b, n, like):
+        """Rotating pinned staging buffers for assembled batches (a fresh pin_memory() per batch costs more host time
+        than the training step it feeds). A yielded batch stays valid until _SLOTS - 1 further batches were drawn."""
+        key = (tuple(like.shape), like.dtype)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage_key = key
+            self._stage = [torch.empty((self.bs,) + tuple(like.shape), dtype=like.dtype).pin_memory()
+                           for _ in range(self._SLOTS)]
+        return self._stage[b % self._SLOTS][:n]
 
 
 def sample_rrc_params(height: int, width: int, generator: torch.Generator, scale=(0.08, 1.0),

@@ -18,6 +18,7 @@ optionally replayed from a CUDA graph) with one host synchronisation per step in
 from __future__ import annotations
 
 import math
+import os
 import os.path as osp
 from typing import Dict, List, Optional
 
@@ -350,7 +351,34 @@ class MaPLe(TrainerX):
         self.lr_history = [self.optim.lr]
 
     # ------------------------------------------------------------------ step
+    def _prefetch_batch(self, batch):
+        """H2D copy of an assembled batch on a side stream (run_epoch: while the previous step computes) into one of
+        two persistent device staging sets. The batch dict then carries device tensors and the event
+        parse_batch_train waits for. A set is rewritten two batches later, after the step that read it was synced."""
+        if not isinstance(batch, dict) or os.environ.get("MFK_NO_PREFETCH"):
+            return batch
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._pf_bufs, self._pf_slot = {}, 0
+        self._pf_slot ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            for k in ("img", "img_u8", "label"):
+                v = batch.get(k)
+                if torch.is_tensor(v) and not v.is_cuda:
+                    key = (k, self._pf_slot, tuple(v.shape), v.dtype)
+                    dst = self._pf_bufs.get(key)
+                    if dst is None:
+                        dst = self._pf_bufs[key] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    dst.copy_(v, non_blocking=True)
+                    batch[k] = dst
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        batch["_h2d_event"] = ev
+        return batch
+
     def parse_batch_train(self, batch):
+        if isinstance(batch, dict) and batch.get("_h2d_event") is not None:
+            torch.cuda.current_stream().wait_event(batch.pop("_h2d_event"))
         if isinstance(batch, dict) and "img_u8" in batch:
             # GpuAugment loader (client_datamanager.GpuAugment): raw uint8 images + host-drawn crop boxes / flips;
             # random_resized_crop + flip + normalize run on the device
@@ -429,6 +457,11 @@ class MaPLe(TrainerX):
 
     def forward_backward(self, batch):
         """fwd + bwd + clip_grad_norm_(1.0) + SGD step (trainers/maple.py:547-627) with a single host sync."""
+        self._fb_enqueue(batch)
+        return self._fb_finish()
+
+    def _fb_enqueue(self, batch):
+        """First half of forward_backward: H2D copy of the batch + the whole step, enqueued without a host sync."""
         image, label, caption = self.parse_batch_train(batch)
         if caption is not None and isinstance(caption, list) and any(c is not None for c in caption):
             raise NotImplementedError("caption branch is out of scope (SURVEY.md §2 #11)")
@@ -436,6 +469,9 @@ class MaPLe(TrainerX):
         image = image.to(F32).contiguous()
         label = label.to(torch.int64).contiguous()
         self.step_async(image, label)
+
+    def _fb_finish(self):
+        """Second half: the one D2H read / stream sync of the step, then the reference's error behaviour."""
         loss, norm, flag = self.read_step_result()
         if flag & 1:
             raise ValueError("NaN values in input image")  # trainers/maple.py:532-535
@@ -449,13 +485,24 @@ class MaPLe(TrainerX):
         return {"loss": loss}
 
     def run_epoch(self, epoch):
+        """trainers/maple.py:629-658. Software-pipelined: while the GPU runs step k the host assembles batch k + 1
+        (stack into pinned staging, augmentation parameters), so the loader's host time hides behind the step
+        instead of adding to it; results, error behaviour and the order of updates are those of the plain loop."""
         self.model.train()
         total, steps = 0.0, 0
-        for batch_idx, batch in enumerate(self.dm.train_loader):
+        it = iter(self.dm.train_loader)
+        batch = next(it, None)
+        batch_idx = 0
+        while batch is not None:
             self.batch_idx = batch_idx
-            out = self.forward_backward(batch)
+            self._fb_enqueue(batch)
+            batch = next(it, None)  # host-side assembly of the next batch overlaps the step just enqueued,
+            if batch is not None:   # and so does its H2D copy (side stream)
+                batch = self._prefetch_batch(batch)
+            out = self._fb_finish()
             total += out.get("loss", 0.0)
             steps += 1
+            batch_idx += 1
         self.update_lr()
         acc = self.test().get("accuracy", 0) if getattr(self.dm, "test_loader", None) is not None else 0
         avg = total / max(1, steps)
