@@ -15,6 +15,7 @@ set (trainers/maple.py:447-479) or the prompt-only set.
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -84,6 +85,8 @@ class MapleEngine:
         self.vis.gemm_ws = self._bufs["__gemm_ws__"]
         self._Bmax = 0
         self._text_cache_valid = False
+        self._eval_graphs = {}
+        self.eval_graph = os.environ.get("MFK_EVAL_GRAPH", "1") != "0"
         self.mom_initialized = False
         self.repack_trainable()
 
@@ -548,16 +551,47 @@ class MapleEngine:
                 ft, _, _ = self._text_features(False, (rank * per, (rank + 1) * per))
                 full = torch.empty(self.C, self.E, device=self.dev, dtype=F32)
                 dist.all_gather_into_tensor(full, ft.contiguous())
-                self._ft_cache = full
             else:
                 ft, _, _ = self._text_features(False)
-                self._ft_cache = ft.clone()
+                full = ft
+            # persistent per-engine cache (never in the workspace shared by co-located clients: their prompts
+            # differ); eval graphs hold its address across refreshes
+            if getattr(self, "_ft_cache", None) is None:
+                self._ft_cache = torch.empty(self.C, self.E, device=self.dev, dtype=F32)
+            self._ft_cache.copy_(full)
             self._text_cache_valid = True
+        if cache_text and self.eval_graph and not torch.cuda.is_current_stream_capturing():
+            return self._logits_graphed(img)
+        return self._logits_image_part(img, torch.empty(B, self.C, device=self.dev, dtype=F32))
+
+    def _logits_image_part(self, img, out):
+        """Vision tower + logits head against the cached text features (the per-batch part of evaluation)."""
+        B = img.shape[0]
         fi, _, _ = self._image_features(img, False)
         self._last_fi = fi
-        out = torch.empty(B, self.C, device=self.dev, dtype=F32)
         ws = self._buf("head.ws", (ops.head_workspace_floats(B, self.C, self.E),), F32)
         ops.head_forward_backward(fi, self._ft_cache, self.logit_scale, None, out, None, None, None, ws)
+        return out
+
+    def _logits_graphed(self, img):
+        """The ~250 launches of one evaluation batch replayed from a CUDA graph (one per batch size): eager
+        evaluation is bound by the host's launch rate, not by the GPU. The first batch of a size runs eagerly (it
+        also allocates the workspaces), the graph is captured right after and replayed from then on; prompts and
+        text features live in persistent buffers, so parameter updates do not invalidate it."""
+        B = img.shape[0]
+        ent = self._eval_graphs.get(B)
+        if ent is not None and ent["gen"] == self.buffer_generation:
+            ent["img"].copy_(img, non_blocking=True)
+            ent["graph"].replay()
+            return ent["out"].clone()
+        out = self._logits_image_part(img, torch.empty(B, self.C, device=self.dev, dtype=F32))
+        ent = {"img": img.clone(), "out": torch.empty(B, self.C, device=self.dev, dtype=F32)}
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._logits_image_part(ent["img"], ent["out"])
+        ent["graph"], ent["gen"] = g, self.buffer_generation
+        self._eval_graphs[B] = ent
         return out
 
     # ------------------------------------------------------------------ fp32 mode (parity contract, inference only)

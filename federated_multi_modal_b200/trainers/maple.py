@@ -361,6 +361,13 @@ class MaPLe(TrainerX):
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._pf_bufs, self._pf_slot = {}, 0
         self._pf_slot ^= 1
+        # The set being rewritten was last read by work enqueued before the PREVIOUS prefetch call (two batches ago):
+        # the copy stream waits for the main-stream position recorded then — not for the step enqueued since.
+        prev = getattr(self, "_pf_main_ev", None)
+        if prev is not None:
+            self._copy_stream.wait_event(prev)
+        self._pf_main_ev = torch.cuda.Event()
+        self._pf_main_ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self._copy_stream):
             for k in ("img", "img_u8", "label"):
                 v = batch.get(k)
@@ -515,13 +522,31 @@ class MaPLe(TrainerX):
 
     @torch.no_grad()
     def test(self, evaluate_train=False):
+        """trainers/maple.py:660-681. Pipelined like run_epoch: batch k + 1 is assembled and copied H2D (side stream)
+        while batch k is evaluated; hits are counted on the device and read back once per call (the reference
+        synchronises per batch). The host never runs more than two batches ahead of the copies (the loader's pinned
+        staging rotates over three)."""
         self.model.eval()
-        correct = total = 0
-        for batch in self.dm.test_loader:
+        total = 0
+        correct = torch.zeros((), device=self.device, dtype=torch.int64)
+        it = iter(self.dm.test_loader)
+        batch = next(it, None)
+        if batch is not None:
+            batch = self._prefetch_batch(batch)
+        h2d = []
+        while batch is not None:
+            ev = batch.get("_h2d_event") if isinstance(batch, dict) else None
             x, y, _ = self.parse_batch_train(batch)
             preds = self.model_inference(x).argmax(dim=1)
-            correct += int((preds == y).sum())
+            correct += (preds == y).sum()
             total += int(y.size(0))
+            h2d.append(ev)
+            if len(h2d) >= 2 and h2d[-2] is not None:
+                h2d[-2].synchronize()
+            batch = next(it, None)
+            if batch is not None:
+                batch = self._prefetch_batch(batch)
+        correct = int(correct)
         acc = 100.0 * correct / total if total else 0.0
         print(f"[Client {self.client_id}] Test Accuracy: {acc:.2f}%")
         return {"accuracy": acc}

@@ -207,3 +207,37 @@ def test_inference_c5_shape_1000_classes():
     got = lg[:4].cpu()[:, pick]
     # same normalisation as everywhere else: error relative to the largest |logit| of the batch
     assert (got - ref).abs().max().item() < 2e-2 * lg.abs().max().item()
+
+
+def test_eval_graph_replay_equals_eager_across_updates_and_clients(c1):
+    """Evaluation batches are replayed from a CUDA graph after the first one: results must be bit-identical to the
+    eager launches, follow parameter updates (prompts / text features live in persistent buffers the graph points
+    to), and co-located clients that share the workspace must keep separate text-feature caches."""
+    G, sd, tok, img, lab = c1
+    img, lab = img.cuda(), lab.cuda()
+    img2 = synth.make_batch(img.shape[0], 10, 77)[0].cuda()
+    eng = MapleEngine(sd, tok)
+    ref = MapleEngine(sd, tok)
+    ref.eval_graph = False
+    a0 = eng.logits(img)            # eager + capture
+    a1 = eng.logits(img2)           # replay
+    a2 = eng.logits(img)            # replay
+    assert eng._eval_graphs and torch.equal(a0, a2)
+    assert torch.equal(a0, ref.logits(img)) and torch.equal(a1, ref.logits(img2))
+    for e in (eng, ref):            # a training step changes prompts, LayerNorms and resblocks.11
+        e.forward_backward(img, lab)
+        e.sgd_step(lr=0.01)
+    b = eng.logits(img2)
+    assert torch.equal(b, ref.logits(img2)) and not torch.equal(b, a1)
+    # second client on the same GPU sharing frozen weights + workspace, with different prompts
+    other = MapleEngine(sd, tok, share_from=eng)
+    other.params[: other.n_update].mul_(0.5)
+    other.repack_trainable()
+    other._text_cache_valid = False
+    c_other = other.logits(img)
+    c_eng = eng.logits(img)
+    assert not torch.equal(c_other, c_eng)
+    ref2 = MapleEngine(sd, tok)
+    ref2.eval_graph = False
+    ref2.params.copy_(eng.params); ref2.repack_trainable(); ref2._text_cache_valid = False
+    assert torch.equal(c_eng, ref2.logits(img))

@@ -178,3 +178,37 @@ def test_federated_rounds_single_gpu_bit_exact_average():
     sds[1][k][0, 0] = float("inf")
     assert not fed.check_weights_valid(sds[1])
     fed.broadcast_weights(avg)
+
+
+def test_pipelined_epoch_and_eval_match_plain_loops():
+    """run_epoch / test() overlap batch assembly + H2D (side stream, rotating staging) with the running step; they
+    must give exactly what the plain per-batch loops give: same parameters bit for bit, same accuracy."""
+    import contextlib, io
+    names = synth.synthetic_classnames(10)
+    items = synthetic_client_items(10, 3, seed=5, classnames=names)              # 30 images
+    cfg = synth.make_cfg()
+    cfg.DATALOADER = synth._NS(TRAIN_X=synth._NS(BATCH_SIZE=4), TEST=synth._NS(BATCH_SIZE=4))
+    outs = []
+    for pipelined in (True, False):
+        dm = ClientDataManager(items[:22], [], items[20:], cfg)                  # 5 train batches, 3 test batches (4,4,2)
+        t = _trainer(False)
+        t.dm = dm
+        with contextlib.redirect_stdout(io.StringIO()):
+            if pipelined:
+                t.run_epoch(0)
+                acc = t.test()["accuracy"]
+            else:
+                t.model.train()
+                for batch in dm.train_loader:
+                    t.forward_backward(batch)
+                t.update_lr()
+                t.model.eval()
+                hit = tot = 0
+                for batch in dm.test_loader:
+                    x, y, _ = t.parse_batch_train(batch)
+                    hit += int((t.model_inference(x).argmax(1) == y).sum()); tot += int(y.numel())
+                acc = 100.0 * hit / tot
+        torch.cuda.synchronize()
+        outs.append((t.model.engine.params.clone(), acc))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
