@@ -417,6 +417,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // a pair CTA keeps only its half of every B tile
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kSubBytes = kABytes + 64 * BK * 2;  // one k-block of a 64-wide tile: A + 8 KB of B (1024-B multiple)
+  constexpr bool kDoubleNarrow = !kMN && !kPair && kStageBytes >= 2 * kSubBytes;  // the 256-wide instantiations
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -495,6 +497,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t tx = kABytes + (uint32_t)w * BK * 2;
         int rem_idx = 0, kb0 = 0, kb1 = num_kb;
         if (kSplitK) decode_slice(p, t, num_kb, rem_idx, kb0, kb1);
+        // Narrow tail tiles (w <= 64) are bound by the TMA round trip, not by the tensor core: a 24 KB k-block per
+        // 48 KB stage leaves only 4 x 24 KB in flight (~480 cycles per k-block). They carry TWO k-blocks per stage.
+        if (kDoubleNarrow && w == 64 && !(kSplitK && p.splitk > 0 && t >= p.full_tiles)) {
+          for (int kb = kb0; kb < kb1; kb += 2) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const int nsub = min(2, kb1 - kb);
+            uint8_t* sa = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nsub * tx);
+            for (int sub = 0; sub < nsub; ++sub) {
+              tma_load_2d(&tmA, &full_bar[stage], sa + sub * kSubBytes, (kb + sub) * BK, m0);
+              tma_load_2d(&tmB, &full_bar[stage], sa + sub * kSubBytes + kABytes, (kb + sub) * BK, n0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kb == kb0 || kb == kb1 - 1) { GTRACE(0, trc); ++trc; }
@@ -547,6 +565,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         int rem_idx = 0, kb0 = 0, kb1 = num_kb;
         if (kSplitK) decode_slice(p, t, num_kb, rem_idx, kb0, kb1);
+        if (kDoubleNarrow && w == 64 && !(kSplitK && p.splitk > 0 && t >= p.full_tiles)) {
+          for (int kb = kb0; kb < kb1; kb += 2) {  // two k-blocks per stage (see the producer)
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (kb == kb0) GTRACE(1, 3 * it + 1);
+            const int nsub = min(2, kb1 - kb);
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint32_t sa = smem_u32(smem + stage * kStageBytes + sub * kSubBytes);
+              const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+              for (int k = 0; k < BK / UK; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || sub > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);
+          GTRACE(1, 3 * it + 2);
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
