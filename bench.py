@@ -394,12 +394,13 @@ def run_ours(args):
             "gpu_launches": kernels_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": 13357824 + 11776,
-                         "traffic_note": "dram read+write bytes of ONE launch (QKV projection 6368x2304x768) from "
-                                         "profiles/r01_gemm_qkv_v10_ncu_raw.csv (ncu --set full); algorithmic operand "
-                                         "bytes A+B = 13.3 MB, the 29 MB bf16 output stays in L2 for the consumer; the "
-                                         "K=3072 split-K dgrad reads 43.9 MB = its operands "
-                                         "(profiles/r01_gemm_fcdgrad_splitk_v10_ncu_raw.csv)",
+                         "frac": achieved / peak_tf, "traffic": 13360896 + 5376,
+                         "traffic_note": "dram read+write bytes of ONE launch (QKV projection 6368x2304x768, in situ: "
+                                         "layer 0 of a real step) from profiles/r01_gemm_layer0_v16_ncu_raw.csv (ncu "
+                                         "--set full); algorithmic operand bytes A+B = 13.3 MB, the 29 MB bf16 output "
+                                         "stays in L2 for the consumer. Same capture: c_fc+QuickGELU 14.5 MB read + "
+                                         "25.2 MB written (evict-first pre-activations), c_proj (split-K) 63.5 MB = A + "
+                                         "fp32 residual + weights, out_proj 30.6 MB",
                          "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA)", "peak_source": peak_src,
                          "how": "96 real-operand vision GEMM launches x 5, CUDA events on the launching stream",
                          "us_per_launch": probe["us_per_launch"], "flops_per_launch": probe["flops_per_launch"],
