@@ -159,3 +159,50 @@ def test_rrc_param_sampling_matches_torchvision():
     for _ in range(50):
         want = RandomResizedCrop.get_params(img, scale=[0.08, 1.0], ratio=[3.0 / 4.0, 4.0 / 3.0])
         assert sample_rrc_params(200, 260, g) == tuple(want)
+
+
+def test_client_datamanager_loader_host_logic():
+    """ClientDataManager (reference trainers/client_datamanager.py:15-112): label validation errors, class bookkeeping,
+    train loader = shuffled + drop_last with a seeded order, test loader = in order and complete."""
+    import pytest
+    from federated_multi_modal_b200.trainers import ClientDataManager, Datum
+    names = synth.synthetic_classnames(3)
+    items = [Datum(impath=f"synthetic://{i}", label=i % 3, classname=names[i % 3], img=torch.full((3, 4, 4), float(i)))
+             for i in range(10)]
+    cfg = synth.make_cfg()
+    cfg.DATALOADER = synth._NS(TRAIN_X=synth._NS(BATCH_SIZE=4), TEST=synth._NS(BATCH_SIZE=4))
+    dm = ClientDataManager(items, [], items[:6], cfg)
+    assert dm.num_classes == 3 and dm.lab2cname == {0: names[0], 1: names[1], 2: names[2]}
+    assert len(dm.train_loader) == 2 and len(dm.test_loader) == 2          # 10 // 4 (drop_last) and ceil(6 / 4)
+    ep = [[int(b["img"][j, 0, 0, 0]) for j in range(b["img"].shape[0])] for b in dm.train_loader]
+    assert [len(b) for b in ep] == [4, 4] and len({i for b in ep for i in b}) == 8
+    dm2 = ClientDataManager(items, [], items[:6], cfg)
+    assert ep == [[int(b["img"][j, 0, 0, 0]) for j in range(4)] for b in dm2.train_loader]   # seeded order
+    te = [b["label"].tolist() for b in dm.test_loader]
+    assert te == [[0, 1, 2, 0], [1, 2]]
+    for b in dm.test_loader:
+        assert b["img"].dtype == torch.float32 and b["label"].dtype == torch.int64
+    class StrLabel:
+        classname, label = "a", "0"
+    with pytest.raises(TypeError):
+        ClientDataManager([StrLabel()], [], [], cfg)
+    class NoLabel:
+        classname = "a"
+    with pytest.raises(ValueError):
+        ClientDataManager([NoLabel()], [], [], cfg)
+
+
+def test_fedavg_exchange_host_side_validity_flags():
+    """Single-process exchange on CPU tensors: publish -> gather carries [ok, n_samples, NaN/Inf flag] per client, the
+    flag word follows check_weights_valid (trainers/maple_fed.py:317-325): bit 0 = NaN, bit 1 = Inf."""
+    from federated_multi_modal_b200.fed import FedAvgExchange
+    ex = FedAvgExchange(8, 3, "cpu")
+    good = torch.arange(8, dtype=torch.float32)
+    nan = good.clone(); nan[2] = float("nan")
+    both = good.clone(); both[1] = float("inf"); both[5] = float("nan")
+    ex.publish(0, good, ok=True, n_samples=5)
+    ex.publish(1, nan, ok=True, n_samples=6)
+    ex.publish(2, both, ok=False, n_samples=7)
+    rows = ex.gather()
+    assert len(rows) == 3 and torch.equal(rows[0], good)
+    assert ex.status.tolist() == [[1.0, 5.0, 0.0], [1.0, 6.0, 1.0], [0.0, 7.0, 3.0]]
