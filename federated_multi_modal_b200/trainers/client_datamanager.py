@@ -39,12 +39,18 @@ class _Loader:
         for b in range(len(self)):
             idx = order[b * self.bs:(b + 1) * self.bs]
             if self.gpu_aug is not None:  # raw uint8 batch + host-drawn augmentation parameters; pixels on the GPU
-                raw = torch.stack([self.items[i].img for i in idx])
-                assert raw.dtype == torch.uint8, "GpuAugment expects uint8 [3,H,W] item images"
+                imgs = [self.items[i].img for i in idx]
+                assert imgs[0].dtype == torch.uint8, "GpuAugment expects uint8 [3,H,W] item images"
+                same = all(im.shape == imgs[0].shape for im in imgs)
+                if torch.cuda.is_available() and same:
+                    raw = torch.stack(imgs, out=self._staging(b, len(imgs), imgs[0]))  # straight into pinned memory
+                else:
+                    raw = torch.stack(imgs)
                 boxes, flip = self.gpu_aug.draw(len(idx), raw.shape[-2], raw.shape[-1])
                 lab = torch.tensor([self.items[i].label for i in idx], dtype=torch.long)
                 if torch.cuda.is_available():
-                    raw, lab, boxes, flip = raw.pin_memory(), lab.pin_memory(), boxes.pin_memory(), flip.pin_memory()
+                    raw = raw if raw.is_pinned() else raw.pin_memory()
+                    lab, boxes, flip = lab.pin_memory(), boxes.pin_memory(), flip.pin_memory()
                 yield {"img_u8": raw, "rrc_box": boxes, "flip": flip, "label": lab, "augment": self.gpu_aug,
                        "impath": [self.items[i].impath for i in idx]}
                 continue
