@@ -61,6 +61,7 @@ SIGNATURES = {
     "mfk_head_workspace_floats": [I, I, I],
     "mfk_head_forward_backward": [P, P, P, P, P, P, P, P, P, I, I, I, P],
     "mfk_fedavg_reduce": [P, P, F, I, L, I, P, P, P, P],
+    "mfk_fedavg_reduce_scatter": [P, P, F, I, L, L, L, P, P, I, P],
     "mfk_check_finite": [P, L, I, P, P],
     "mfk_grad_norm": [P, L, P, P, P],
     "mfk_sgd_step": [P, P, P, L, P, P, P],

@@ -92,6 +92,64 @@ fedavg_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ we
   }
 }
 
+// Sharded form of the same reduction for W ranks (one 8xB200 box): this rank reduces elements [lo, hi) only — same
+// per-element order, so the values are those of fedavg_kernel bit for bit — and PUSHES the result into every rank's
+// output buffers (peer pointers over NVLink). Per rank (W-1)/W * n * (4 + 4 + 2) bytes cross NVLink instead of
+// (W-1) * n * 4 for the gather form. fp32 inputs; lo is a multiple of 4.
+__global__ void __launch_bounds__(256)
+fedavg_scatter_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ weights, int K, long long n,
+                      long long lo, long long hi, float divisor, float* const* __restrict__ out32,
+                      __half* const* __restrict__ out16, int W) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
+    float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 chunk = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const float* p = static_cast<const float*>(ptrs[k]);
+      float4 v;
+      if (i + 3 < n) {
+        v = load4<float>(p, i);
+      } else {
+        v.x = p[i];
+        v.y = i + 1 < n ? p[i + 1] : 0.f;
+        v.z = i + 2 < n ? p[i + 2] : 0.f;
+        v.w = 0.f;
+      }
+      bool bn = false, bi = false;
+      v.x = sanitize(v.x, nullptr, bn, bi); v.y = sanitize(v.y, nullptr, bn, bi);
+      v.z = sanitize(v.z, nullptr, bn, bi); v.w = sanitize(v.w, nullptr, bn, bi);
+      if (weights) {
+        const float w = weights[k];
+        v.x = __fmul_rn(v.x, w); v.y = __fmul_rn(v.y, w); v.z = __fmul_rn(v.z, w); v.w = __fmul_rn(v.w, w);
+      }
+      const int pos = k & 15;
+      if (pos == 0) chunk = v;
+      else { chunk.x = __fadd_rn(chunk.x, v.x); chunk.y = __fadd_rn(chunk.y, v.y); chunk.z = __fadd_rn(chunk.z, v.z); chunk.w = __fadd_rn(chunk.w, v.w); }
+      if (pos == 15 || k == K - 1) {
+        if (k / 16 == 0) total = chunk;
+        else { total.x = __fadd_rn(total.x, chunk.x); total.y = __fadd_rn(total.y, chunk.y); total.z = __fadd_rn(total.z, chunk.z); total.w = __fadd_rn(total.w, chunk.w); }
+      }
+    }
+    float4 m;
+    m.x = __fdiv_rn(total.x, divisor); m.y = __fdiv_rn(total.y, divisor);
+    m.z = __fdiv_rn(total.z, divisor); m.w = __fdiv_rn(total.w, divisor);
+    const __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
+    const float mm[4] = {m.x, m.y, m.z, m.w};
+    for (int r = 0; r < W; ++r) {
+      if (i + 3 < n) {
+        *reinterpret_cast<float4*>(out32[r] + i) = m;
+        *reinterpret_cast<uint2*>(out16[r] + i) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      } else {
+        for (int e = 0; e < 4 && i + e < n; ++e) {
+          out32[r][i + e] = mm[e];
+          out16[r][i + e] = __float2half_rn(mm[e]);
+        }
+      }
+    }
+  }
+}
+
 template <typename TIN>
 __global__ void check_finite_kernel(const TIN* __restrict__ p, long long n, int* __restrict__ flag, bool vec) {
   bool bn = false, bi = false;
@@ -195,6 +253,23 @@ extern "C" int mfk_fedavg_reduce(const void* const* client_ptrs_dev, const float
     fedavg_kernel<__half><<<(unsigned)blocks, 256, 0, ST(stream)>>>(client_ptrs_dev, weights_dev, K, n, divisor, out_f32, static_cast<__half*>(out_f16), flags_dev);
   else
     fedavg_kernel<float><<<(unsigned)blocks, 256, 0, ST(stream)>>>(client_ptrs_dev, weights_dev, K, n, divisor, out_f32, static_cast<__half*>(out_f16), flags_dev);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_fedavg_reduce_scatter(const void* const* client_ptrs_dev, const float* weights_dev, float divisor,
+                                         int K, long long n, long long lo, long long hi,
+                                         float* const* out_f32_ptrs_dev, void* const* out_f16_ptrs_dev, int W,
+                                         void* stream) {
+  if (!client_ptrs_dev || !out_f32_ptrs_dev || !out_f16_ptrs_dev || K <= 0 || W <= 0 || n <= 0 || !(divisor > 0.f))
+    return MFK_EARG;
+  if (lo < 0 || hi > n || (lo & 3)) return MFK_ESHAPE;
+  if (hi <= lo) return MFK_OK;  // empty shard
+  long long blocks = ((hi - lo + 3) / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fedavg_scatter_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(client_ptrs_dev, weights_dev, K, n, lo, hi, divisor,
+                                                                  out_f32_ptrs_dev,
+                                                                  reinterpret_cast<__half* const*>(out_f16_ptrs_dev), W);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

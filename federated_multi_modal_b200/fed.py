@@ -8,6 +8,10 @@ Transports for the client tensors (flat fp32 arenas of the trainable parameters)
   "p2p"  — symmetric-memory buffers: every rank's reduce kernel loads the peers' rows straight over
            NVLink (peer pointers in the kernel's pointer table), i.e. transfer and weighted reduction are
            ONE kernel; a symmetric-memory barrier on each side orders it against the producers.
+  "p2p_sharded" — the all-reduce-shaped form of the same thing (opt-in, cfg.FED.TRANSPORT): rank r reduces only elements
+           [r*n/W, (r+1)*n/W) of the K rows (same per-element order => bit-identical) and pushes the fp32 / fp16 result
+           into every rank's output buffer with peer stores (`mfk_fedavg_reduce_scatter`): (W-1)/W * 10 bytes per
+           element over NVLink instead of (W-1) * 4.
   "nccl" — torch.distributed all_gather_into_tensor, then the same reduce kernel on local rows
            (also the path used with the gloo backend in CPU tests of the host logic).
 No ring/tree all-reduce is used: its summation order differs from the reference's (not bit-exact).
@@ -44,15 +48,32 @@ class FedAvgExchange:
         cuda = self.dev.type == "cuda"
         if transport == "auto":
             self.transport = "p2p" if (cuda and self.world > 1 and dist.get_backend() == "nccl") else "nccl"
-        if self.transport == "p2p" and self.world > 1:
+        self._sharded = None
+        if self.transport == "p2p_sharded" and self.world == 1:
+            self.transport = "p2p"
+        if self.transport in ("p2p", "p2p_sharded") and self.world > 1:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 self.send = symm_mem.empty(k_local * n, device=self.dev, dtype=torch.float32)
                 self._symm = symm_mem.rendezvous(self.send, dist.group.WORLD)
                 self.send = self.send.view(k_local, n)
+                if self.transport == "p2p_sharded":
+                    # outputs live in symmetric memory too: every rank's kernel stores its shard into all of them
+                    o32 = symm_mem.empty(n, device=self.dev, dtype=torch.float32)
+                    h32 = symm_mem.rendezvous(o32, dist.group.WORLD)
+                    o16 = symm_mem.empty(n, device=self.dev, dtype=torch.float16)
+                    h16 = symm_mem.rendezvous(o16, dist.group.WORLD)
+                    p32 = [h32.get_buffer(r, (n,), torch.float32) for r in range(self.world)]
+                    p16 = [h16.get_buffer(r, (n,), torch.float16) for r in range(self.world)]
+                    per = ((n + self.world - 1) // self.world + 3) // 4 * 4
+                    self._sharded = dict(
+                        out32=o32, out16=o16, keep=(h32, h16, p32, p16),
+                        p32=torch.tensor([t.data_ptr() for t in p32], dtype=torch.int64, device=self.dev),
+                        p16=torch.tensor([t.data_ptr() for t in p16], dtype=torch.int64, device=self.dev),
+                        lo=min(n, self.rank * per), hi=min(n, (self.rank + 1) * per))
             except Exception as e:  # noqa: BLE001 — symmetric memory unavailable: use the NCCL transport
                 print(f"[fed] symmetric memory unavailable ({type(e).__name__}: {e}); using nccl all_gather")
-                self.transport = "nccl"
+                self.transport, self._symm, self._sharded = "nccl", None, None
         if self._symm is None:
             self.send = torch.zeros(k_local, n, device=self.dev, dtype=torch.float32)
         self.gathered = None if self._symm is not None else torch.zeros(self.K, n, device=self.dev,
@@ -61,7 +82,9 @@ class FedAvgExchange:
         self.status_local = torch.zeros(k_local, 3, device=self.dev, dtype=torch.float32)
         self.status = torch.zeros(self.K, 3, device=self.dev, dtype=torch.float32)
         self.flags_local = torch.zeros(k_local, device=self.dev, dtype=torch.int32)
-        if cuda:
+        if self._sharded is not None:
+            self.out32, self.out16 = self._sharded["out32"], self._sharded["out16"]
+        elif cuda:
             self.out32 = torch.zeros(n, device=self.dev, dtype=torch.float32)
             self.out16 = torch.zeros(n, device=self.dev, dtype=torch.float16)
 
@@ -118,7 +141,12 @@ class FedAvgExchange:
             div = float(sum(float(status[k, 1]) for k in valid))
         else:
             w, div = None, float(len(valid))
-        ops.fedavg_reduce(ptrs, w, div, len(valid), self.n, False, self.out32, self.out16, None)
+        if self._sharded is not None:
+            sh = self._sharded
+            ops.fedavg_reduce_scatter(ptrs, w, div, len(valid), self.n, sh["lo"], sh["hi"], sh["p32"], sh["p16"],
+                                      self.world)
+        else:
+            ops.fedavg_reduce(ptrs, w, div, len(valid), self.n, False, self.out32, self.out16, None)
         if self._symm is not None:
             self._symm.barrier()  # peers may overwrite their send buffers only after everyone has read them
         return self.out32, self.out16, valid, bad

@@ -276,6 +276,12 @@ def fedavg_reduce(ptrs_dev, weights_dev, divisor, K, n, in_is_fp16, out_f32, out
          flags_dev, stream_ptr())
 
 
+def fedavg_reduce_scatter(ptrs_dev, weights_dev, divisor, K, n, lo, hi, out32_ptrs_dev, out16_ptrs_dev, W):
+    """Sharded fixed-order FedAvg: this rank reduces [lo, hi) and pushes the result into all W ranks' buffers."""
+    call("mfk_fedavg_reduce_scatter", ptrs_dev, weights_dev, float(divisor), K, n, lo, hi, out32_ptrs_dev,
+         out16_ptrs_dev, W, stream_ptr())
+
+
 def check_finite(t, flag_dev):
     code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[t.dtype]
     call("mfk_check_finite", t, t.numel(), code, flag_dev, stream_ptr())

@@ -212,6 +212,13 @@ int mfk_head_forward_backward(const float* img_feat, const float* txt_feat, cons
  * their sum). flags_dev (optional, K ints, caller zeroes): bit0 = client had NaN, bit1 = client had Inf.  */
 int mfk_fedavg_reduce(const void* const* client_ptrs_dev, const float* weights_dev, float divisor, int K,
                       long long n, int in_is_fp16, float* out_f32, void* out_f16, int* flags_dev, void* stream);
+/* Sharded form for W ranks of one NVLink box: reduces elements [lo, hi) (lo % 4 == 0) of the K fp32 client rows in the
+ * same fixed order (bit-identical values) and stores them into EVERY rank's output buffers — out_f32_ptrs_dev /
+ * out_f16_ptrs_dev are device arrays of W (peer) pointers to n-element buffers. Replaces safe_average_weights +
+ * broadcast_weights traffic (trainers/maple_fed.py:309-339) with (W-1)/W * 10 bytes per element over NVLink.       */
+int mfk_fedavg_reduce_scatter(const void* const* client_ptrs_dev, const float* weights_dev, float divisor, int K,
+                              long long n, long long lo, long long hi, float* const* out_f32_ptrs_dev,
+                              void* const* out_f16_ptrs_dev, int W, void* stream);
 /* check_weights_valid: ORs bit0 (NaN) / bit1 (Inf) into *flag_dev. dtype 0 f32, 1 f16, 2 bf16.       */
 int mfk_check_finite(const void* p, long long n, int dtype, int* flag_dev, void* stream);
 

@@ -30,12 +30,12 @@ def test_client_assignment():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+@pytest.mark.parametrize("transport", ["p2p", "p2p_sharded", "nccl"])
 def test_fedavg_exchange_nccl(transport):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     r = _torchrun(min(n, 8), "nccl", transport, port=29551 if transport == "p2p" else 29552)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
-    if transport == "p2p":
-        assert "transport=p2p" in r.stdout, r.stdout[-2000:]
+    if transport.startswith("p2p"):  # no silent fallback to the all-gather transport
+        assert f"transport={transport}\n" in r.stdout + "\n", r.stdout[-2000:]
