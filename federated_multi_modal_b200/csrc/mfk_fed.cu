@@ -263,8 +263,9 @@ extern "C" int mfk_fedavg_reduce_scatter(const void* const* client_ptrs_dev, con
                                          void* stream) {
   if (!client_ptrs_dev || !out_f32_ptrs_dev || !out_f16_ptrs_dev || K <= 0 || W <= 0 || n <= 0 || !(divisor > 0.f))
     return MFK_EARG;
-  if (lo < 0 || hi > n || (lo & 3)) return MFK_ESHAPE;
-  if (hi <= lo) return MFK_OK;  // empty shard
+  if (lo < 0 || hi > n) return MFK_ESHAPE;
+  if (hi <= lo) return MFK_OK;  // empty shard (ranks beyond the end of a short tensor)
+  if (lo & 3) return MFK_ESHAPE;
   long long blocks = ((hi - lo + 3) / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   fedavg_scatter_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(client_ptrs_dev, weights_dev, K, n, lo, hi, divisor,

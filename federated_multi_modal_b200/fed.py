@@ -38,6 +38,14 @@ def clients_of_rank(num_clients: int, rank: int, world: int) -> List[int]:
     return list(range(rank * k, (rank + 1) * k))
 
 
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Elements [lo, hi) reduced by `rank` in the sharded exchange: equal shards rounded up to a multiple of 4 (the
+    kernel works on float4 groups), the last ranks' shards clipped at n (possibly empty). The shards of all ranks
+    tile [0, n) exactly."""
+    per = ((n + world - 1) // world + 3) // 4 * 4
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
 class FedAvgExchange:
     def __init__(self, n: int, k_local: int, device, transport: str = "auto"):
         self.rank, self.world = dist_info()
@@ -65,12 +73,12 @@ class FedAvgExchange:
                     h16 = symm_mem.rendezvous(o16, dist.group.WORLD)
                     p32 = [h32.get_buffer(r, (n,), torch.float32) for r in range(self.world)]
                     p16 = [h16.get_buffer(r, (n,), torch.float16) for r in range(self.world)]
-                    per = ((n + self.world - 1) // self.world + 3) // 4 * 4
+                    lo, hi = shard_range(n, self.rank, self.world)
                     self._sharded = dict(
                         out32=o32, out16=o16, keep=(h32, h16, p32, p16),
                         p32=torch.tensor([t.data_ptr() for t in p32], dtype=torch.int64, device=self.dev),
                         p16=torch.tensor([t.data_ptr() for t in p16], dtype=torch.int64, device=self.dev),
-                        lo=min(n, self.rank * per), hi=min(n, (self.rank + 1) * per))
+                        lo=lo, hi=hi)
             except Exception as e:  # noqa: BLE001 — symmetric memory unavailable: use the NCCL transport
                 print(f"[fed] symmetric memory unavailable ({type(e).__name__}: {e}); using nccl all_gather")
                 self.transport, self._symm, self._sharded = "nccl", None, None

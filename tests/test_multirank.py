@@ -29,6 +29,16 @@ def test_client_assignment():
         clients_of_rank(10, 0, 4)
 
 
+def test_sharded_exchange_ranges_tile_the_arena():
+    from federated_multi_modal_b200.fed import shard_range
+    for n in (1, 3, 4, 5, 64, 12352, 13856768, 13856771):
+        for world in (1, 2, 3, 4, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(lo <= hi and (lo % 4 == 0 or lo == hi) for lo, hi in r)     # non-empty shards start on a float4
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))   # contiguous, no overlap, no gap
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("transport", ["p2p", "p2p_sharded", "nccl"])
 def test_fedavg_exchange_nccl(transport):
