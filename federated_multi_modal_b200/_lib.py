@@ -64,7 +64,7 @@ SIGNATURES = {
     "mfk_fedavg_reduce_scatter": [P, P, F, I, L, L, L, P, P, I, P],
     "mfk_check_finite": [P, L, I, P, P],
     "mfk_grad_norm": [P, L, P, P, P],
-    "mfk_sgd_step": [P, P, P, L, P, P, P],
+    "mfk_sgd_step": [P, P, P, L, P, P, P, P, P],
 }
 _RET = {"mfk_error_string": ctypes.c_char_p, "mfk_head_workspace_floats": L}
 _NO_STATUS = {"mfk_version", "mfk_error_string", "mfk_head_workspace_floats", "mfk_ln_bwd_ctas",
@@ -84,8 +84,13 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         if not os.path.exists(LIB_PATH):
             if not build_if_missing:
                 raise RuntimeError(f"{LIB_PATH} is missing: run `python -m federated_multi_modal_b200.csrc.build`")
+            # one builder at a time: N ranks of a torchrun job may all find the library missing
+            import fcntl
             from .csrc.build import build
-            build()
+            with open(LIB_PATH + ".lock", "w") as lk:
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                if not os.path.exists(LIB_PATH):
+                    build()
         lib = ctypes.CDLL(LIB_PATH)
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

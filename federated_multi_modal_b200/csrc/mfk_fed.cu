@@ -20,6 +20,13 @@ __device__ __forceinline__ float sanitize(float v, int* flag, bool& bad_nan, boo
   return v;
 }
 
+// Pointer-table entries are caller data the entry point cannot inspect (device memory), so the kernels test the
+// alignment of every vector access themselves and fall back to element loads / stores (rows at
+// base + j*n*4 with n % 4 != 0, or arbitrary state_dict data_ptr()s).
+template <typename T>
+__device__ __forceinline__ bool vec_ok(const T* p, long long i) {
+  return (reinterpret_cast<uintptr_t>(p + i) & (4 * sizeof(T) - 1)) == 0;
+}
 template <typename TIN>
 __device__ __forceinline__ float4 load4(const TIN* p, long long i);
 template <>
@@ -45,8 +52,10 @@ fedavg_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ we
     for (int k = 0; k < K; ++k) {
       const TIN* p = static_cast<const TIN*>(ptrs[k]);
       float4 v;
-      if (i + 3 < n) {
+      if (i + 3 < n && vec_ok(p, i)) {
         v = load4<TIN>(p, i);
+      } else if (i + 3 < n) {
+        v = make_float4((float)p[i], (float)p[i + 1], (float)p[i + 2], (float)p[i + 3]);
       } else {
         v.x = (float)p[i];
         v.y = i + 1 < n ? (float)p[i + 1] : 0.f;
@@ -76,7 +85,7 @@ fedavg_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ we
     float4 m;
     m.x = __fdiv_rn(total.x, divisor); m.y = __fdiv_rn(total.y, divisor);
     m.z = __fdiv_rn(total.z, divisor); m.w = __fdiv_rn(total.w, divisor);
-    if (i + 3 < n) {
+    if (i + 3 < n && (!out32 || vec_ok(out32, i)) && (!out16 || vec_ok(out16, i))) {
       if (out32) *reinterpret_cast<float4*>(out32 + i) = m;
       if (out16) {
         __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
@@ -107,8 +116,10 @@ fedavg_scatter_kernel(const void* const* __restrict__ ptrs, const float* __restr
     for (int k = 0; k < K; ++k) {
       const float* p = static_cast<const float*>(ptrs[k]);
       float4 v;
-      if (i + 3 < n) {
+      if (i + 3 < n && vec_ok(p, i)) {
         v = load4<float>(p, i);
+      } else if (i + 3 < n) {
+        v = make_float4(p[i], p[i + 1], p[i + 2], p[i + 3]);
       } else {
         v.x = p[i];
         v.y = i + 1 < n ? p[i + 1] : 0.f;
@@ -136,7 +147,7 @@ fedavg_scatter_kernel(const void* const* __restrict__ ptrs, const float* __restr
     const __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
     const float mm[4] = {m.x, m.y, m.z, m.w};
     for (int r = 0; r < W; ++r) {
-      if (i + 3 < n) {
+      if (i + 3 < n && vec_ok(out32[r], i) && vec_ok(out16[r], i)) {
         *reinterpret_cast<float4*>(out32[r] + i) = m;
         *reinterpret_cast<uint2*>(out16[r] + i) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
@@ -207,12 +218,23 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int P, flo
 }
 // torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.SGD.step (trainers/maple.py:592-598).
 // hp = {lr, momentum, dampening, weight_decay, max_norm, nesterov, first_step}
+// Guard: the reference raises on a NaN/Inf input image (trainers/maple.py:556-557) or total loss
+// (375-376) BEFORE optim.step(), so its parameters and momentum stay intact; the fused step therefore skips the
+// whole update when *loss_dev is non-finite or *flag_dev != 0. A non-finite gradient norm with a finite loss does
+// reach optim.step() in the reference (error_if_nonfinite=False): torch.clamp propagates the NaN coefficient
+// (fminf would return 1), reproduced here.
 __global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom, long long n,
-                                const float* __restrict__ hp, const float* __restrict__ total_norm) {
+                                const float* __restrict__ hp, const float* __restrict__ total_norm,
+                                const float* __restrict__ loss_dev, const int* __restrict__ flag_dev) {
+  if (loss_dev && !isfinite(loss_dev[0])) return;
+  if (flag_dev && flag_dev[0] != 0) return;
   const float lr = hp[0], mu = hp[1], damp = hp[2], wd = hp[3], max_norm = hp[4];
   const bool nesterov = hp[5] != 0.f, first = hp[6] != 0.f;
   float coef = 1.f;
-  if (max_norm > 0.f) coef = fminf(max_norm / (total_norm[0] + 1e-6f), 1.f);
+  if (max_norm > 0.f) {
+    const float c = max_norm / (total_norm[0] + 1e-6f);
+    coef = isnan(c) ? c : fminf(c, 1.f);
+  }
   auto upd = [&](float& pv, float& gv, float& mv) {
     const float gc = gv * coef;
     gv = gc;  // grads are clipped in place, as clip_grad_norm_ does
@@ -298,13 +320,14 @@ extern "C" int mfk_grad_norm(const float* g, long long n, float* partial_ws, flo
 }
 
 extern "C" int mfk_sgd_step(float* p, float* g, float* mom, long long n, const float* hyper_dev,
-                            const float* total_norm_dev, void* stream) {
+                            const float* total_norm_dev, const float* loss_dev, const int* flag_dev, void* stream) {
   if (!p || !g || !mom || n <= 0 || !hyper_dev || !total_norm_dev) return MFK_EARG;
   if (!mfk_aligned16(p) || !mfk_aligned16(g) || !mfk_aligned16(mom)) return MFK_EALIGN;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  sgd_step_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(p, g, mom, n, hyper_dev, total_norm_dev);
+  sgd_step_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(p, g, mom, n, hyper_dev, total_norm_dev, loss_dev,
+                                                            flag_dev);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

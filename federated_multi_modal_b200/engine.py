@@ -771,7 +771,8 @@ class MapleEngine:
     # ------------------------------------------------------------------ optimizer
     @torch.no_grad()
     def sgd_step(self, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, dampening: float = 0.0,
-                 nesterov: bool = False, max_norm: float = 1.0, hyper: Optional[torch.Tensor] = None):
+                 nesterov: bool = False, max_norm: float = 1.0, hyper: Optional[torch.Tensor] = None,
+                 loss_dev: Optional[torch.Tensor] = None, flag_dev: Optional[torch.Tensor] = None):
         """clip_grad_norm_(max_norm) over all gradients + SGD on the updated region of the arena
         (trainers/maple.py:592-598), then refresh bf16 copies of trainable block weights."""
         n = self.n_update
@@ -781,7 +782,7 @@ class MapleEngine:
             hyper = torch.tensor([lr, momentum, dampening, weight_decay, max_norm, float(nesterov),
                                   0.0 if self.mom_initialized else 1.0], device=self.dev, dtype=F32)
         ops.grad_norm(self.grads[:n], ws, norm)
-        ops.sgd_step(self.params[:n], self.grads[:n], self.momentum[:n], hyper, norm, n)
+        ops.sgd_step(self.params[:n], self.grads[:n], self.momentum[:n], hyper, norm, n, loss_dev, flag_dev)
         self.mom_initialized = True
         self.repack_trainable()
         return norm
@@ -808,6 +809,52 @@ class MapleEngine:
             if k in self.p:
                 self.p[k].copy_(v.to(self.dev, F32))
         self.repack_trainable()
+
+    @torch.no_grad()
+    def reload_state_dict(self, state_dict: Dict[str, torch.Tensor]):
+        """CustomCLIP.load_state_dict(strict=True) replaces EVERY tensor (trainers/maple_fed.py:327-331), not only the
+        trainable ones: refresh, in place, the arena, logit_scale, the prompt prefix / suffix embeddings and every
+        packed frozen tensor (bf16 + transposed block weights, biases, conv1, class / positional embeddings, the two
+        projections). Addresses are kept, so captured CUDA graphs stay valid; the text-feature cache and the fp32-mode
+        split-weight caches are dropped. Frozen packs are shared by co-located clients (share_from): loading the same
+        global state_dict into each of them, as broadcast_weights does, rewrites the shared copy with equal values."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("clip_model2.")}
+        dev = self.dev
+        f32 = lambda k: sd[k].detach().to(dev, F32)
+        for k, dst in self.p.items():
+            if k in sd:
+                dst.copy_(f32(k).view(dst.shape))
+        self.logit_scale.copy_(f32("logit_scale").reshape(1))
+        self.prefix.copy_(f32("prompt_learner.token_prefix"))
+        self.suffix.copy_(f32("prompt_learner.token_suffix"))
+        for tw in (self.vis, self.txt):
+            for l in range(tw.L):
+                pre = f"{tw.name}.transformer.resblocks.{l}."
+                w = tw.w[l]
+                for lin in _LIN:
+                    w.pop(lin + ".w3", None)
+                    if lin + ".master" in w:
+                        continue  # lives in the arena (copied above); bf16 copies come from repack_trainable()
+                    wk, bk = _lin_keys(lin)
+                    W = f32(pre + wk)
+                    w[lin + ".w"].copy_(W)
+                    w[lin + ".wT"].copy_(W.t())
+                    w[lin + ".b"].copy_(f32(pre + bk))
+        v, t = "image_encoder.", "text_encoder."
+        conv = f32(v + "conv1.weight")
+        self.conv_w.copy_(conv.reshape(conv.shape[0], -1))
+        self.cls.copy_(f32(v + "class_embedding"))
+        self.vpos.copy_(f32(v + "positional_embedding"))
+        proj = f32(v + "proj")
+        self.vproj.copy_(proj)
+        self.vproj_T.copy_(self._split_b(proj.t()))
+        self.tpos.copy_(f32(t + "positional_embedding"))
+        tp = f32(t + "text_projection")
+        self.tproj.copy_(tp)
+        self.tproj_T.copy_(self._split_b(tp.t()))
+        self._conv_w3 = None
+        self._sd_src.update(sd)  # references (fp32 mode re-reads the exact frozen weights)
+        self.repack_trainable()  # also invalidates the text-feature cache
 
     def flops_per_step(self, B: int) -> float:
         """Algorithmic FLOPs of one fwd+bwd step for the work actually performed."""

@@ -47,7 +47,9 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class FedAvgExchange:
-    def __init__(self, n: int, k_local: int, device, transport: str = "auto"):
+    def __init__(self, n: int, k_local: int, device, transport: str = "auto", strict_transport: bool = False):
+        """``strict_transport``: raise instead of downgrading to the NCCL all-gather when the requested NVLink
+        transport cannot be set up (bench.py and the trainer's cfg.FED.STRICT_TRANSPORT use it)."""
         self.rank, self.world = dist_info()
         self.n, self.k_local, self.K = n, k_local, k_local * self.world
         self.dev = torch.device(device)
@@ -59,33 +61,52 @@ class FedAvgExchange:
         self._sharded = None
         if self.transport == "p2p_sharded" and self.world == 1:
             self.transport = "p2p"
+        # rows start on 16-byte boundaries whatever n is (the reduce kernels vectorise by 4 elements)
+        self.n_pad = n_pad = (n + 3) // 4 * 4
+        self.requested_transport = self.transport
         if self.transport in ("p2p", "p2p_sharded") and self.world > 1:
+            err = None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                self.send = symm_mem.empty(k_local * n, device=self.dev, dtype=torch.float32)
-                self._symm = symm_mem.rendezvous(self.send, dist.group.WORLD)
-                self.send = self.send.view(k_local, n)
+                self._send_flat = symm_mem.empty(k_local * n_pad, device=self.dev, dtype=torch.float32)
+                self._symm = symm_mem.rendezvous(self._send_flat, dist.group.WORLD)
+                self.send = self._send_flat.view(k_local, n_pad)[:, :n]
                 if self.transport == "p2p_sharded":
                     # outputs live in symmetric memory too: every rank's kernel stores its shard into all of them
-                    o32 = symm_mem.empty(n, device=self.dev, dtype=torch.float32)
+                    o32 = symm_mem.empty(n_pad, device=self.dev, dtype=torch.float32)
                     h32 = symm_mem.rendezvous(o32, dist.group.WORLD)
-                    o16 = symm_mem.empty(n, device=self.dev, dtype=torch.float16)
+                    o16 = symm_mem.empty(n_pad, device=self.dev, dtype=torch.float16)
                     h16 = symm_mem.rendezvous(o16, dist.group.WORLD)
-                    p32 = [h32.get_buffer(r, (n,), torch.float32) for r in range(self.world)]
-                    p16 = [h16.get_buffer(r, (n,), torch.float16) for r in range(self.world)]
+                    p32 = [h32.get_buffer(r, (n_pad,), torch.float32) for r in range(self.world)]
+                    p16 = [h16.get_buffer(r, (n_pad,), torch.float16) for r in range(self.world)]
                     lo, hi = shard_range(n, self.rank, self.world)
                     self._sharded = dict(
-                        out32=o32, out16=o16, keep=(h32, h16, p32, p16),
+                        out32=o32[:n], out16=o16[:n], keep=(h32, h16, p32, p16),
                         p32=torch.tensor([t.data_ptr() for t in p32], dtype=torch.int64, device=self.dev),
                         p16=torch.tensor([t.data_ptr() for t in p16], dtype=torch.int64, device=self.dev),
                         lo=lo, hi=hi)
-            except Exception as e:  # noqa: BLE001 — symmetric memory unavailable: use the NCCL transport
-                print(f"[fed] symmetric memory unavailable ({type(e).__name__}: {e}); using nccl all_gather")
+            except Exception as e:  # noqa: BLE001 — decided collectively below
+                err = e
+            # The transport is chosen by ALL ranks together: a rank that falls back on its own would sit in an NCCL
+            # all_gather while its peers wait in the symmetric-memory barrier (deadlock at the first round end).
+            # A rank whose rendezvous raised while others are still inside it cannot be helped here — symmetric-memory
+            # rendezvous is itself collective and fails on every rank or none in practice.
+            ok = torch.tensor([0 if err is not None else 1], device=self.dev, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if strict_transport:
+                    raise RuntimeError(f"FedAvgExchange: transport '{self.transport}' unavailable on at least one rank "
+                                       f"(this rank: {type(err).__name__ if err else 'ok'}: {err}); refusing the silent "
+                                       "downgrade to nccl all_gather (strict_transport=True)")
+                print(f"[fed] symmetric memory unavailable on at least one rank ({type(err).__name__ if err else 'peer'}"
+                      f": {err}); all ranks use nccl all_gather")
                 self.transport, self._symm, self._sharded = "nccl", None, None
         if self._symm is None:
-            self.send = torch.zeros(k_local, n, device=self.dev, dtype=torch.float32)
-        self.gathered = None if self._symm is not None else torch.zeros(self.K, n, device=self.dev,
-                                                                         dtype=torch.float32)
+            self._send_flat = torch.zeros(k_local * n_pad, device=self.dev, dtype=torch.float32)
+            self.send = self._send_flat.view(k_local, n_pad)[:, :n]
+        self._gathered_flat = None if self._symm is not None else torch.zeros(self.K * n_pad, device=self.dev,
+                                                                               dtype=torch.float32)
+        self.gathered = None if self._symm is not None else self._gathered_flat.view(self.K, n_pad)[:, :n]
         # per client: [ok, n_samples, NaN/Inf flag word of its published tensor (1 = NaN, 2 = Inf)]
         self.status_local = torch.zeros(k_local, 3, device=self.dev, dtype=torch.float32)
         self.status = torch.zeros(self.K, 3, device=self.dev, dtype=torch.float32)
@@ -126,10 +147,10 @@ class FedAvgExchange:
             self._symm.barrier()
             rows = []
             for r in range(self.world):
-                peer = self._symm.get_buffer(r, (self.k_local, self.n), torch.float32)
-                rows += [peer[j] for j in range(self.k_local)]
+                peer = self._symm.get_buffer(r, (self.k_local, self.n_pad), torch.float32)
+                rows += [peer[j, : self.n] for j in range(self.k_local)]
             return rows
-        dist.all_gather_into_tensor(self.gathered.view(-1), self.send.view(-1))
+        dist.all_gather_into_tensor(self._gathered_flat, self._send_flat)
         return [self.gathered[k] for k in range(self.K)]
 
     # -------------------------------------------------------------------- stage 2: fixed-order reduce (CUDA)

@@ -291,5 +291,8 @@ def grad_norm(g, partial_ws, norm_out):
     call("mfk_grad_norm", g, g.numel(), partial_ws, norm_out, stream_ptr(), kernels=2)
 
 
-def sgd_step(p, g, mom, hyper_dev, total_norm_dev, n=None):
-    call("mfk_sgd_step", p, g, mom, p.numel() if n is None else n, hyper_dev, total_norm_dev, stream_ptr())
+def sgd_step(p, g, mom, hyper_dev, total_norm_dev, n=None, loss_dev=None, flag_dev=None):
+    """loss_dev (fp32 [1]) / flag_dev (int32 [1]): optional device-side guard — a non-finite loss or a raised input
+    flag skips the update (the reference raises before optim.step(), trainers/maple.py:375-376, 556-557)."""
+    call("mfk_sgd_step", p, g, mom, p.numel() if n is None else n, hyper_dev, total_norm_dev, loss_dev, flag_dev,
+         stream_ptr())

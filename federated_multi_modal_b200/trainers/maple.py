@@ -240,7 +240,9 @@ class CustomCLIP(nn.Module):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._arena_newer = False
         if self.engine is not None:
-            self.engine.load_trainable({n: p.detach() for n, p in self._grad_params})
+            # every key reaches the kernels, not only the tensors with requires_grad: logit_scale, prompt
+            # prefix / suffix, embeddings, frozen block weights, and in prompt_only mode the LN / resblocks.11 weights
+            self.engine.reload_state_dict(nn.Module.state_dict(self))
             self._versions = self._param_versions()
         return out
 
@@ -412,7 +414,8 @@ class MaPLe(TrainerX):
         eng = self.model.engine
         eng.forward_backward(img, lab, loss_out=self._readback[0:1])
         ops.check_finite(img, self._flag)
-        norm = eng.sgd_step(0.0, hyper=self._hyper_dev)
+        # device-side guard: a NaN/Inf image or loss skips the update (the reference raises before optim.step())
+        norm = eng.sgd_step(0.0, hyper=self._hyper_dev, loss_dev=self._readback[0:1], flag_dev=self._flag)
         self._readback[1:2].copy_(norm)
 
     def step_async(self, image, label):
@@ -450,6 +453,9 @@ class MaPLe(TrainerX):
             self._static_lab.copy_(label, non_blocking=True)
             self._graph.replay()
             eng.mom_initialized = True
+            # the replayed step moved ctx / deep prompts / LN / resblocks.11: cached text features are stale (the
+            # Python flag writes inside forward_backward ran at capture time only)
+            eng._text_cache_valid = False
         else:
             self._step_kernels(image, label)
         model._arena_newer = True

@@ -224,10 +224,13 @@ int mfk_check_finite(const void* p, long long n, int dtype, int* flag_dev, void*
 
 /* ------------------------------------------------------------------ clip_grad_norm_ + SGD (trainers/maple.py:592-598)
  * norm_out[0] = ||g||_2 (fixed-order reduction; partial_ws: 296 floats).
- * hyper_dev = {lr, momentum, dampening, weight_decay, max_norm, nesterov, first_step} as 7 floats.    */
+ * hyper_dev = {lr, momentum, dampening, weight_decay, max_norm, nesterov, first_step} as 7 floats.
+ * loss_dev / flag_dev (both optional): the update is skipped on the device when *loss_dev is NaN/Inf or
+ * *flag_dev != 0 — the reference raises before optim.step() in those cases (trainers/maple.py:556-557, 375-376),
+ * leaving parameters and momentum untouched. A NaN gradient norm propagates like torch.clamp does.       */
 int mfk_grad_norm(const float* g, long long n, float* partial_ws, float* norm_out, void* stream);
 int mfk_sgd_step(float* p, float* g, float* mom, long long n, const float* hyper_dev,
-                 const float* total_norm_dev, void* stream);
+                 const float* total_norm_dev, const float* loss_dev, const int* flag_dev, void* stream);
 
 #ifdef __cplusplus
 }

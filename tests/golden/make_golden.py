@@ -10,6 +10,17 @@ Outputs (small, committed): tests/golden/*.pt
   c3s_fp32.pt  C=38 classes / B=2, same content (text-heavy shape of config 3).
   fedavg.pt    MaPLeFederated.safe_average_weights / check_weights_valid known answers at
                K = 2, 3, 8, 16, 17, 32, 33 incl. NaN/Inf entries.
+  c2_fp32.pt   BASELINE config 2 (B=32, C=10): the shape bench.py measures. Same content as c1.
+  c4s_fp32.pt  BASELINE config 4 per-client step shape (B=64, C=21). Same content.
+  traj_fp32.pt 3-step training trajectories of the reference (CustomCLIP + clip_grad_norm_(1.0) +
+               torch.optim.SGD(momentum 0.9, wd 5e-4), trainers/maple.py:588-598) at B=4, C=10 for the yaml's
+               LR 0.0026 and for LR 0.05: per-step losses / grad norms and the final values of every
+               prompt-learner tensor + strided samples of the other trainable tensors. Also the loss
+               sequence of the reference AS-IS (PREC=fp16: SGD applied to fp16 parameters in place) to
+               quantify the fp32-master vs fp16-in-place difference.
+  ckpt_spec.pt the checkpoint dict MaPLeFederated.save_model hands to Dassl's save_checkpoint
+               (trainers/maple_fed.py:367-386): target directory, top-level keys, and key/shape/dtype of
+               the state_dict before and after one safe_average_weights aggregation.
 Inputs are regenerated from seeds by federated_multi_modal_b200.synth on any box.
 """
 import os
@@ -110,9 +121,103 @@ def fedavg_cases():
     return cases
 
 
+def trajectory(lr, steps=3, B=4, C=10, fp32=True, seed_batch=500):
+    """The reference's own step (trainers/maple.py:588-598) repeated: model(image, label) -> zero_grad ->
+    backward -> clip_grad_norm_(model.parameters(), 1.0) -> optim.step(), Dassl's SGD defaults."""
+    torch.manual_seed(0)
+    cfg = synth.make_cfg()
+    model = rh.build_reference_customclip(synth.random_clip_state_dict(0), synth.synthetic_classnames(C), cfg,
+                                          synth.random_prompt_learner_state(1), fp32=fp32)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=lr, momentum=0.9, weight_decay=5e-4, dampening=0, nesterov=False)
+    init = {n: p.detach().float().clone() for n, p in model.named_parameters() if p.requires_grad}
+    losses, norms = [], []
+    for s in range(steps):
+        img, lab = synth.make_batch(B, C, seed_batch + s)
+        loss = model(img if fp32 else img.half(), lab)
+        opt.zero_grad()
+        loss.backward()
+        norms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0, error_if_nonfinite=False)))
+        opt.step()
+        losses.append(float(loss))
+    out = dict(meta=dict(B=B, C=C, lr=lr, steps=steps, seed_batch=seed_batch, fp32=fp32, momentum=0.9,
+                         weight_decay=5e-4), losses=losses, grad_norms=norms)
+    if fp32:
+        model.eval()
+        with torch.no_grad():
+            img, _ = synth.make_batch(B, C, seed_batch + steps)
+            out["logits_after"] = model(img).float().clone()
+        out["final"], out["delta"] = {}, {}
+        for n, p in model.named_parameters():
+            if p.requires_grad and n in init:
+                out["final"][n] = pack_grad(p)          # full below 64k elements, strided sample + norm above
+                out["delta"][n] = pack_grad(p.detach().float() - init[n])
+    return out
+
+
+def checkpoint_spec():
+    """What MaPLeFederated.save_model builds (trainers/maple_fed.py:367-386), captured by swapping the (stubbed)
+    Dassl save_checkpoint of the imported reference module for a recorder."""
+    import types
+    _, _, fed = rh.load_reference()
+    cfg = synth.make_cfg()
+    m = rh.build_reference_customclip(synth.random_clip_state_dict(0), synth.synthetic_classnames(10), cfg,
+                                      synth.random_prompt_learner_state(1), fp32=False)
+    sd0 = m.state_dict()
+    averaged = fed.MaPLeFederated.safe_average_weights(None, [sd0, sd0], [0, 1])
+    got = {}
+    made = []
+    saved = (fed.save_checkpoint, fed.mkdir_if_missing)
+    fed.save_checkpoint = lambda state, d, is_best=False, **kw: got.update(state=state, dir=d, is_best=is_best)
+    fed.mkdir_if_missing = lambda d: made.append(d)
+    try:
+        fake = types.SimpleNamespace(
+            cfg=types.SimpleNamespace(OUTPUT_DIR="OUT", VERBOSE=False, OPTIM=types.SimpleNamespace(MAX_EPOCH=2),
+                                      dump=lambda: "cfg-dump"),
+            global_weights=averaged)
+        fed.MaPLeFederated.save_model(fake, directory="OUT")
+    finally:
+        fed.save_checkpoint, fed.mkdir_if_missing = saved
+    st = got["state"]
+    spec = lambda d: [(k, tuple(v.shape), str(v.dtype)) for k, v in d.items()]
+    return dict(target_dir=got["dir"], made_dirs=made, top_keys=list(st.keys()), epoch=st["epoch"],
+                optimizer=st["optimizer"], scheduler=st["scheduler"], cfg=st["cfg"],
+                spec_before_aggregation=spec(sd0), spec_after_aggregation=spec(st["state_dict"]),
+                logit_scale_after=st["state_dict"]["logit_scale"].clone(),
+                ctx_after=st["state_dict"]["prompt_learner.ctx"].clone())
+
+
+def extra_cases():
+    torch.set_num_threads(8)
+    o2, _ = run_case(32, 10, seed_batch=2032)
+    torch.save(o2, os.path.join(HERE, "c2_fp32.pt"))
+    print("c2 loss", o2["loss"].item())
+    o4, _ = run_case(64, 21, seed_batch=4064)
+    torch.save(o4, os.path.join(HERE, "c4s_fp32.pt"))
+    print("c4s loss", o4["loss"].item())
+    tr = {"lr0.0026": trajectory(0.0026), "lr0.05": trajectory(0.05),
+          "lr0.0026_fp16_as_is": trajectory(0.0026, fp32=False), "lr0.05_fp16_as_is": trajectory(0.05, fp32=False)}
+    torch.save(tr, os.path.join(HERE, "traj_fp32.pt"))
+    for k, v in tr.items():
+        print(k, "losses", v["losses"], "norms", v["grad_norms"])
+    torch.save(checkpoint_spec(), os.path.join(HERE, "ckpt_spec.pt"))
+
+
+if __name__ == "__main__" and "--extra-only" in sys.argv:
+    import contextlib, io
+    with contextlib.redirect_stderr(io.StringIO()):
+        extra_cases()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+    sys.exit(0)
+
+
 if __name__ == "__main__":
     import contextlib, io
     torch.set_num_threads(8)
+    extra_cases()
     o, _ = run_case(4, 10)
     torch.save(o, os.path.join(HERE, "c1_fp32.pt"))
     print("c1 loss", o["loss"].item(), "grads", o["n_with_grad"], "/", o["n_trainable"])
