@@ -217,13 +217,22 @@ class MaPLeFederated(TrainerX):
         eng = self.clients[0].model.engine
         self.global_arena = eng.params[: eng.n_update].clone()
 
+    def _global_state_dict(self):
+        """The aggregator's ``global_weights`` in the reference's wire layout: all 634 keys; after at least one
+        aggregation EVERY tensor is fp16 because ``safe_average_weights`` ends in ``.half()``
+        (trainers/maple_fed.py:314) — before that, the model's own dtypes (fp16 weights, fp32 LN / embeddings)."""
+        sd = self.clients[0].model.state_dict()
+        if _fed(self.cfg, "REFERENCE_FP16_CAST", True) and self.nan_stats["total_updates"] > 0:
+            sd = type(sd)((k, v.half() if v.is_floating_point() else v) for k, v in sd.items())
+        return sd
+
     def finalize_training(self):
         print("\nTraining Summary:")
         print(f"Completed Rounds: {self.nan_stats['total_updates']}")
         print(f"Skipped Rounds: {self.nan_stats['skipped_rounds']}")
         fail_rate = len(self.nan_stats["failed_clients"]) / max(1, self.num_clients)
         print(f"Client failure rate: {fail_rate:.2%}")
-        self.global_weights = self.clients[0].model.state_dict()
+        self.global_weights = self._global_state_dict()
         out_dir = getattr(self.cfg, "OUTPUT_DIR", "")
         if out_dir and self.rank == 0:
             self.save_model(directory=out_dir)

@@ -206,3 +206,63 @@ def test_fedavg_exchange_host_side_validity_flags():
     rows = ex.gather()
     assert len(rows) == 3 and torch.equal(rows[0], good)
     assert ex.status.tolist() == [[1.0, 5.0, 0.0], [1.0, 6.0, 1.0], [0.0, 7.0, 3.0]]
+
+
+def test_checkpoint_wire_format_matches_reference(tmp_path):
+    """MaPLeFederated.save_model (reference trainers/maple_fed.py:367-386): directory layout, top-level keys and the
+    key / shape / dtype list of the saved state_dict equal what the unmodified reference hands to Dassl's
+    save_checkpoint after one aggregation (tests/golden/ckpt_spec.pt, recorded from the reference); values that are
+    determined by the seeds (ctx from the token embedding, logit_scale) are equal too. File round trip through
+    Dassl's ``model.pth.tar-<epoch>`` naming and MaPLe.load_model's key filtering are checked on the host."""
+    import types
+    from federated_multi_modal_b200.dassl_compat import load_checkpoint, save_checkpoint
+    from federated_multi_modal_b200.trainers import MaPLe, MaPLeFederated
+    spec = load_golden("ckpt_spec.pt")
+    m = _model()
+    fed = MaPLeFederated.__new__(MaPLeFederated)
+    fed.cfg = types.SimpleNamespace(OUTPUT_DIR=str(tmp_path), VERBOSE=False, OPTIM=types.SimpleNamespace(MAX_EPOCH=2),
+                                    dump=lambda: "cfg-dump", FED=types.SimpleNamespace(REFERENCE_FP16_CAST=True))
+    fed.clients = [types.SimpleNamespace(model=m)]
+    fed.nan_stats = {"total_updates": 0, "failed_clients": [], "skipped_rounds": 0}
+    before = fed._global_state_dict()
+    assert [(k, tuple(v.shape), str(v.dtype)) for k, v in before.items()] == spec["spec_before_aggregation"]
+    fed.nan_stats["total_updates"] = 1          # one safe_average_weights happened: every tensor is fp16 from here on
+    fed.global_weights = fed._global_state_dict()
+    path = fed.save_model(directory=str(tmp_path))
+    want_dir = os.path.join(str(tmp_path), os.path.basename(spec["target_dir"]))
+    assert os.path.basename(spec["target_dir"]) == "MultiModalPromptLearner_Aggregator"
+    assert path == os.path.join(want_dir, f"model.pth.tar-{spec['epoch']}") and os.path.exists(path)
+    assert open(os.path.join(want_dir, "checkpoint")).read().strip() == os.path.basename(path)
+    ck = load_checkpoint(path)
+    assert list(ck.keys()) == spec["top_keys"]
+    assert (ck["epoch"], ck["optimizer"], ck["scheduler"], ck["cfg"]) == (spec["epoch"], None, None, "cfg-dump")
+    assert [(k, tuple(v.shape), str(v.dtype)) for k, v in ck["state_dict"].items()] == spec["spec_after_aggregation"]
+    assert torch.equal(ck["state_dict"]["logit_scale"], spec["logit_scale_after"])
+    assert torch.equal(ck["state_dict"]["prompt_learner.ctx"], spec["ctx_after"])
+    # a reference-written checkpoint (all fp16) loads into the module with the reference's strict=True semantics,
+    # restoring the module's own dtypes
+    m2 = _model()
+    with torch.no_grad():
+        m2.prompt_learner.ctx.add_(1.0)
+    m2.load_state_dict(ck["state_dict"], strict=True)
+    sd2 = torch.nn.Module.state_dict(m2)
+    assert [(k, str(v.dtype)) for k, v in sd2.items()] == [(k, d) for k, _, d in spec["spec_before_aggregation"]]
+    assert torch.equal(sd2["prompt_learner.ctx"], ck["state_dict"]["prompt_learner.ctx"])
+    # MaPLe.load_model (trainers/maple.py:683-716): per-model sub-directory, token_prefix / token_suffix dropped,
+    # non-strict load; missing file -> FileNotFoundError
+    t = MaPLe.__new__(MaPLe)
+    m3 = _model(C=4)                            # other class list: the buffers must NOT be taken from the checkpoint
+    t._models = {"MultiModalPromptLearner_0": m3}
+    t.get_model_names = lambda names=None: list(t._models)
+    sd = {k: v for k, v in ck["state_dict"].items()}
+    save_checkpoint({"epoch": 2, "state_dict": sd}, os.path.join(str(tmp_path), "MultiModalPromptLearner_0"))
+    prefix_before = m3.prompt_learner.token_prefix.clone()
+    with torch.no_grad():
+        m3.prompt_learner.ctx.zero_()
+    t.load_model(str(tmp_path), epoch=2)
+    assert torch.equal(m3.prompt_learner.ctx, ck["state_dict"]["prompt_learner.ctx"])
+    assert torch.equal(m3.prompt_learner.token_prefix, prefix_before) and prefix_before.shape[0] == 4
+    with pytest.raises(FileNotFoundError):
+        t.load_model(str(tmp_path), epoch=7)
+    with pytest.raises(FileNotFoundError):
+        fed.load_model(str(tmp_path), epoch=9)

@@ -181,6 +181,18 @@ def test_top1_agreement_against_oracle_256_images():
         confident += int(conf.sum()); confident_agree += int((same & conf).sum())
     print(f"top-1 agreement raw {agree}/{total}, margin-filtered {confident_agree}/{confident}, "
           f"worst logit rel err {worst:.2e}")
+    # the raw number is recorded, not only printed (gpurun_out/parity_report.jsonl -> profiles/)
+    import json, os
+    from helpers import REPO
+    d = os.environ.get("MFK_REPORT_DIR", os.path.join(REPO, "gpurun_out"))
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": "top1_agreement_256_images", "raw_agree": agree, "total": total,
+                                "margin_filtered_agree": confident_agree, "margin_filtered_total": confident,
+                                "worst_logit_rel_err": worst}) + "\n")
+    except OSError:
+        pass
     assert worst < 2e-2
     assert confident > total // 2
     assert confident_agree == confident          # 100 % where the margin exceeds the bf16 error

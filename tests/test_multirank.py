@@ -45,8 +45,7 @@ def test_fedavg_exchange_nccl(transport):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    # the opt-in sharded transport has been validated at world size 2 so far (round 1); the others run on every GPU
-    world = 2 if transport == "p2p_sharded" else min(n, 8)
+    world = min(n, 8)
     r = _torchrun(world, "nccl", transport, port=29551 if transport == "p2p" else 29552)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     if transport.startswith("p2p"):  # no silent fallback to the all-gather transport
