@@ -47,14 +47,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices):
+        """ONE nvidia-smi process (started by rank 0 only) sampling every GPU of the run."""
+        self.indices, self.proc, self.lines = list(indices), None, []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices),
+                                          f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:  # noqa: BLE001
@@ -81,7 +82,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "gpus_sampled": len(self.indices),
+                "sm_mhz_min": sm[0] if sm else None}
 
 
 def make_trainer(device, graph=True):
@@ -163,8 +165,19 @@ def run_reference(args):
         orc = MapleOracle(sd, tok)
         img, lab = synth.make_batch(sample_B, N_CLS, 7)
 
+        mom = {}
+
         def step():
-            return orc.forward_backward(img, lab)["loss"].item()
+            # the reference's whole step (trainers/maple.py:588-598): fwd + bwd + clip_grad_norm_(1.0) + SGD(momentum
+            # 0.9, wd 5e-4) on the oracle's fp32 parameters
+            out = orc.forward_backward(img, lab)
+            G = out["grads"]
+            coef = min(1.0, 1.0 / (float(torch.sqrt(sum((g.double() ** 2).sum() for g in G.values()))) + 1e-6))
+            for k, g in G.items():
+                d = g * coef + 5e-4 * orc.P[k]
+                mom[k] = d.clone() if k not in mom else mom[k].mul_(0.9).add_(d)
+                orc.P[k].sub_(0.0026 * mom[k])
+            return out["loss"].item()
     for _ in range(max(1, min(args.warmup, 1))):
         step()
     k = max(1, min(args.steps, 3))
@@ -176,57 +189,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
             "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of 8 of the 32 images"},
+            "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of 8 of the 32 images "
+                                                    "(fwd + bwd + clip_grad_norm_ + SGD on all host threads)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": f"{k} steps of {sample_B} images x {N_CLS} classes, fp32, fwd+bwd+clip+SGD"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def gemm_roofline(trainer, batch_dev, n_steps=2):
-    """Per-kernel-class device time of one eager step (CUDA events around every C-ABI call on the launching
-    stream) -> achieved TFLOP/s of the dominant kernel (the tcgen05 GEMM)."""
-    from federated_multi_modal_b200 import _lib
-    recs = []
-    orig = _lib.call
-
-    def timed_call(name, *a, **kw):
-        if name in _lib._NO_STATUS:
-            return orig(name, *a, **kw)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(name, *a, **kw)
-        e.record()
-        fl = 0.0
-        if name == "mfk_gemm_bf16":
-            fl = 2.0 * a[4] * a[5] * a[6]
-        recs.append((name, s, e, fl))
-        return r
-    import federated_multi_modal_b200.ops as ops_mod
-    saved_graph = trainer._use_graph
-    trainer._use_graph = False
-    ops_mod.call = timed_call
-    snap = (trainer.model.engine.params.clone(), trainer.model.engine.momentum.clone())
-    try:
-        for _ in range(n_steps):
-            # park the GPU for ~30 ms so the host queues the whole step ahead: events then time kernels that run
-            # back to back, not the host's launch latency
-            torch.cuda._sleep(int(6e7))
-            trainer.step_async(batch_dev[0], batch_dev[1])
-            torch.cuda.synchronize()
-    finally:
-        ops_mod.call = orig
-        trainer._use_graph = saved_graph
-        trainer.model.engine.params.copy_(snap[0]); trainer.model.engine.momentum.copy_(snap[1])
-        trainer.model.engine.repack_trainable()
-    by = {}
-    for name, s, e, fl in recs:
-        d = by.setdefault(name, [0.0, 0.0, 0])
-        d[0] += s.elapsed_time(e) * 1e-3
-        d[1] += fl
-        d[2] += 1
-    return {k: {"s_per_step": v[0] / n_steps, "flops_per_step": v[1] / n_steps, "calls_per_step": v[2] // n_steps}
-            for k, v in by.items()}
 
 
 def gemm_probe(eng, reps=5):
@@ -312,10 +280,11 @@ def run_ours(args):
     k0 = _lib.kernel_count
     step_dev(0)
     kernels_per_step_eager = _lib.kernel_count - k0  # 0 when replaying a graph: counted at capture instead
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(range(world)) if rank == 0 else None   # one poller for the whole run, not one per rank
+    if sampler:
+        sampler.start()
     t_dev = timed(step_dev, K)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     loss_now, _, _ = trainer.read_step_result()
 
     # ---- end-to-end leg (`e2e`): public trainer API, pinned host batches, H2D + D2H every step
@@ -342,13 +311,18 @@ def run_ours(args):
 
     # ---- FedAvg round-end exchange of the trainable arena (all clients of all ranks), timed separately
     from federated_multi_modal_b200.fed import FedAvgExchange
-    ex = FedAvgExchange(eng.n_update, 1, dev)
+    # strict: a failed NVLink (symmetric-memory) setup raises instead of silently measuring the all-gather transport
+    ex = FedAvgExchange(eng.n_update, 1, dev, transport=args.fed_transport, strict_transport=True)
     def fedavg(i):
         ex.publish(0, eng.params)
         rows = ex.gather()
         ex.reduce(rows)
     fedavg(0)
     t_fed = timed(fedavg, 5) / 5
+
+    # ---- multi-GPU correctness, outside any timed region: every rank compares what the exchange produced from the
+    # clients' REAL trained arenas with the CPU oracle's fixed-order mean of the same gathered rows (checker only)
+    fed_check = fedavg_bitexact_check(ex, eng, dev, world)
 
     # ---- one federated round of this rank's client: 16 local steps + round-end FedAvg exchange + broadcast
     # (load averaged arena, refresh bf16 copies, drop optimiser state) — BASELINE's "FedAvg round time"
@@ -364,10 +338,12 @@ def run_ours(args):
     fed_round(0)
     t_round = timed(fed_round, 2) / 2
 
+    # ---- BASELINE config 4 shape: 4 co-located clients per GPU (21 classes, batch 64, 16 local steps each), round-end
+    # exchange over all 4 x N clients
+    c4 = None if args.no_c4 else c4_round(dev, world, rank, timed, args.fed_transport)
+
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
-        prof = gemm_roofline(trainer, dev_pool[0])
-        g = prof.get("mfk_gemm_bf16", {"s_per_step": float("nan"), "flops_per_step": 0.0})
         probe = gemm_probe(eng)
         # kernels per step: count one eager step's launches
         k0 = _lib.kernel_count
@@ -378,8 +354,13 @@ def run_ours(args):
         step_flops = eng.flops_per_step(B)
         achieved = probe["tflops"]
         cpu, _ = cpu_baseline()
+        fed_roof = fedavg_roofline(eng, dev, peak_hbm)
+        fed_cpu = cpu_fedavg_baseline(eng.n_update)
         value = world * B * K / t_dev
         img_bytes = pool[0]["img"].numel() * 4 + pool[0]["label"].numel() * 8
+        traffic = roofline_traffic()
+        burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops") \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -394,26 +375,32 @@ def run_ours(args):
             "gpu_launches": kernels_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": 13360896 + 5376,
-                         "traffic_note": "dram read+write bytes of ONE launch (QKV projection 6368x2304x768, in situ: "
-                                         "layer 0 of a real step) from profiles/r01_gemm_layer0_v16_ncu_raw.csv (ncu "
-                                         "--set full); algorithmic operand bytes A+B = 13.3 MB, the 29 MB bf16 output "
-                                         "stays in L2 for the consumer. Same capture: c_fc+QuickGELU 14.5 MB read + "
-                                         "25.2 MB written (evict-first pre-activations), c_proj (split-K) 63.5 MB = A + "
-                                         "fp32 residual + weights, out_proj 30.6 MB",
+                         "frac": achieved / peak_tf,
+                         "frac_of_burst_peak": (achieved / burst) if burst else None,
+                         "peak_kind": "sustained bf16 (cuBLAS 8192^3 back to back for 4 s); the probe is a 12 ms chain of "
+                                      "480 launches, so frac_of_burst_peak (best-of-10 cuBLAS) is the stricter reading",
+                         "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_note": traffic["note"] if traffic else "no ncu --set full capture committed",
                          "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA)", "peak_source": peak_src,
                          "how": "96 real-operand vision GEMM launches x 5, CUDA events on the launching stream",
                          "us_per_launch": probe["us_per_launch"], "flops_per_launch": probe["flops_per_launch"],
-                         "gemm_flops_per_step": g["flops_per_step"],
                          "step_flops": step_flops,
-                         "step_frac": step_flops / (t_dev / K) / 1e12 / peak_tf},
+                         "step_frac": step_flops / (t_dev / K) / 1e12 / peak_tf,
+                         "kernel_shares": "per-kernel shares of the step: profiles/ (ncu launch list + "
+                                          "tools/launch_summary.py); not re-derived here — CUDA-event intervals on the "
+                                          "two concurrent tower streams overlap and do not sum to the step"},
             "cpu_baseline": cpu,
             "fedavg_exchange_ms": t_fed * 1e3,
+            "fedavg_transport": ex.transport,
+            "fedavg_bitexact": fed_check["bitexact"],
+            "fedavg_check": fed_check,
+            "fedavg_exchange_nvlink_gbs_per_rank": ((world - 1) * eng.n_update * 4 / t_fed / 1e9) if world > 1 else None,
+            "fedavg_roofline": fed_roof,
+            "fedavg_cpu_baseline": fed_cpu,
             "fedavg_round_s": t_round,
             "fedavg_round_config": f"{world} clients (1 per GPU), {ROUND_STEPS} local steps of batch {B}, all-rank "
                                    f"exchange of the {eng.n_update}-element fp32 trainable arena + broadcast",
-            "kernel_time_breakdown_ms": {k.replace("mfk_", ""): round(v["s_per_step"] * 1e3, 4) for k, v in
-                                         sorted(prof.items(), key=lambda kv: -kv[1]["s_per_step"])},
+            "fed_round_c4": c4,
             "loss": loss_now,
         }
         sys.stdout.flush()
@@ -422,6 +409,151 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not fed_check["bitexact"] or (c4 is not None and not c4.get("fedavg_bitexact", True)):
+        raise SystemExit("bench.py: FedAvg exchange output differs from the fixed-order oracle")
+
+
+def fedavg_bitexact_check(ex, eng, dev, world):
+    """Every rank: publish the real arena (perturbed per rank so the clients differ), exchange, and compare with
+    oracle/maple_cpu.fedavg_oracle on the gathered rows; also that all ranks hold the same bytes. Returns a dict
+    with the AND over ranks. The oracle is only the checker here (never timed, never on the product path)."""
+    import torch.distributed as dist
+    from oracle.maple_cpu import fedavg_oracle
+    rank = dist.get_rank() if world > 1 else 0
+    mine = eng.params[: eng.n_update].clone()
+    mine.mul_(1.0 + 0.03125 * rank).add_(1e-3 * rank)          # distinct, deterministic per-rank client tensors
+    ex.publish(0, mine, ok=True, n_samples=10 + rank)
+    rows = ex.gather()
+    rows_cpu = [r.clone().cpu() for r in rows]
+    ok = True
+    for weighted in (False, True):
+        m32, m16, valid, _ = ex.reduce(rows, weighted=weighted)
+        r32, r16 = fedavg_oracle(rows_cpu, [10.0 + k for k in range(len(rows_cpu))] if weighted else None)
+        ok = ok and len(valid) == len(rows_cpu) and torch.equal(m32.cpu(), r32) and torch.equal(m16.cpu(), r16)
+    chk = m32.double().sum().reshape(1).clone()
+    flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+    same = True
+    if world > 1:
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        same = all(torch.equal(x, lst[0]) for x in lst)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"bitexact": bool(int(flag.item())) and same, "identical_on_all_ranks": same, "clients": len(rows_cpu),
+            "elements": int(eng.n_update), "modes": ["uniform", "sample-count weighted"], "transport": ex.transport,
+            "requested_transport": ex.requested_transport}
+
+
+def fedavg_roofline(eng, dev, peak_hbm):
+    """mfk_fedavg_reduce alone on K client arenas resident in local HBM (K = 2 / 8 / 32): algorithmic bytes
+    (K reads + fp32 write + fp16 write) x n x 4 B over the kernel time (CUDA events, 10 launches; the K x 55 MB
+    inputs exceed L2 from K = 4)."""
+    from federated_multi_modal_b200 import ops
+    n = eng.n_update
+    out = {}
+    base = eng.params[:n]
+    for K in (2, 8, 32):
+        rows = torch.empty(K, n, device=dev, dtype=torch.float32)
+        rows.copy_(base.unsqueeze(0).expand(K, n))
+        rows.mul_(torch.linspace(0.5, 1.5, K, device=dev).unsqueeze(1))
+        ptrs = torch.tensor([rows[k].data_ptr() for k in range(K)], dtype=torch.int64, device=dev)
+        o32 = torch.empty(n, device=dev, dtype=torch.float32)
+        o16 = torch.empty(n, device=dev, dtype=torch.float16)
+        for _ in range(2):
+            ops.fedavg_reduce(ptrs, None, float(K), K, n, False, o32, o16, None)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(10):
+            ops.fedavg_reduce(ptrs, None, float(K), K, n, False, o32, o16, None)
+        e.record()
+        torch.cuda.synchronize()
+        t = s.elapsed_time(e) * 1e-3 / 10
+        byt = (K * 4 + 4 + 2) * n
+        out[f"K{K}"] = {"ms": t * 1e3, "bytes": byt, "achieved_gbs": byt / t / 1e9, "frac": byt / t / 1e9 / peak_hbm}
+        del rows
+    out["bound"], out["peak_gbs"], out["kernel"] = "hbm", peak_hbm, "fedavg_kernel<float> (fixed-order reduce)"
+    return out
+
+
+def cpu_fedavg_baseline(n, threads=None):
+    """safe_average_weights (reference trainers/maple_fed.py:309-315) on the host cores: the oracle's restatement on
+    the trainable arena (n fp32 elements per client) at K = 2 / 8 / 32 — the CPU side of "FedAvg round time"."""
+    from oracle.maple_cpu import fedavg_oracle
+    if threads:
+        torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    base = torch.randn(n, generator=g)
+    out = {"cores": torch.get_num_threads(), "kind": "port", "elements": int(n),
+           "what": "oracle/maple_cpu.fedavg_oracle (fp32 cast, nan_to_num, fixed-order sum, /K, .half()) on K tensors of "
+                   "the trainable arena's size"}
+    for K in (2, 8, 32):
+        rows = [base * (1.0 + 0.01 * k) for k in range(K)]
+        fedavg_oracle(rows[:2])
+        t0 = time.perf_counter()
+        fedavg_oracle(rows)
+        out[f"K{K}_ms"] = (time.perf_counter() - t0) * 1e3
+    return out
+
+
+def roofline_traffic():
+    """DRAM bytes of ONE launch of the dominant kernel from the newest committed ncu --set full capture
+    (profiles/roofline_traffic.json, written by tools/ncu_summary.py from the raw CSV) — not measurable live."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"bytes": d["dram_bytes_per_launch"], "note": d.get("note", "")}
+
+
+def c4_round(dev, world, rank, timed, transport):
+    """BASELINE config 4 on this box: 4 clients per GPU (21 classes, batch 64, 16 local steps per client and round)
+    sharing one frozen CLIP copy and one activation workspace, round-end FedAvg over all 4 x N clients, broadcast."""
+    import torch.distributed as dist
+    from federated_multi_modal_b200 import synth
+    from federated_multi_modal_b200.fed import FedAvgExchange
+    from federated_multi_modal_b200.trainers import MaPLe
+    from oracle.maple_cpu import fedavg_oracle
+    C, Bc, KL, STEPS = 21, 64, 4, 16
+    cfg = synth.make_cfg(n_ctx=N_CTX, depth=DEPTH, prec="bf16")
+    names = synth.synthetic_classnames(C)
+    trainers, share = [], None
+    for j in range(KL):
+        t = MaPLe(cfg, client_id=rank * KL + j, classnames=names, share_engine=share)
+        t.model.train()
+        share = share or t.model.engine
+        trainers.append(t)
+    pool = [tuple(x.to(dev) for x in synth.make_batch(Bc, C, 4000 + 10 * rank + i)) for i in range(2)]
+    n = share.n_update
+    ex = FedAvgExchange(n, KL, dev, transport=transport, strict_transport=True)
+    def one_round(i):
+        for j, t in enumerate(trainers):
+            for s_ in range(STEPS):
+                t.step_async(*pool[(s_ + j) % 2])
+            ex.publish(j, t.model.engine.params)
+        rows = ex.gather()
+        m32, m16, valid, _ = ex.reduce(rows)
+        for t in trainers:
+            e = t.model.engine
+            e.params[:n].copy_(m16)
+            e.repack_trainable()
+            e.reset_optimizer_state()
+    one_round(0)                                   # captures the 4 CUDA graphs
+    rows = ex.gather()
+    rows_cpu = [r.clone().cpu() for r in rows]
+    m32 = ex.reduce(rows)[0]
+    ok = torch.equal(m32.cpu(), fedavg_oracle(rows_cpu)[0])
+    flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    t_round = timed(one_round, 2) / 2
+    def ex_only(i):
+        ex.reduce(ex.gather())
+    t_ex = timed(ex_only, 5) / 5
+    return {"round_s": t_round, "clients": KL * world, "clients_per_gpu": KL, "classes": C, "batch": Bc,
+            "steps_per_client": STEPS, "images_per_s": world * KL * STEPS * Bc / t_round,
+            "exchange_ms": t_ex * 1e3, "transport": ex.transport, "fedavg_bitexact": bool(int(flag.item())),
+            "note": "co-located clients run one after another on shared frozen weights / workspace (device-resident "
+                    "batches, CUDA-graph steps); timed with CUDA events, max over ranks"}
 
 
 def main():
@@ -431,6 +563,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the config-4-shaped federated round (extra key)")
+    ap.add_argument("--fed-transport", default="auto", choices=["auto", "p2p", "p2p_sharded", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
