@@ -611,6 +611,22 @@ struct RepackProblem {  // mirrors mfk.h
   const float* in; bf16* out_t; bf16* copy; int M, N;
   int tile0, tiles_n;  // first global 64x64 tile index of this problem; its tiles per row
 };
+// Rounding of the trainable masters to bf16 is DITHERED with a fixed per-element threshold (hash of the element index)
+// instead of round-to-nearest-even: the reference's weights sit on the fp16 grid, i.e. on only 8 positions inside a
+// bf16 interval, 1/8 of them exactly on the tie. Updates at the yaml's LR (2.6e-3 x clipped gradients) are far below
+// one bf16 ulp, so under RNE the copy seen by the forward GEMMs would not move at all for 7/8 of the elements and
+// jump half an ulp IN THE SIGN OF THE UPDATE for the tie elements — a coherent over-shoot of the whole update
+// (measured: eval logits 2.1e-2 from the fp32 mode at the same parameters after three lr=0.0026 steps, image-feature
+// error 33 % aligned with the text features, against 2e-3 / 6 % at initialisation). A fixed uniform threshold makes
+// the expected rounded value equal to the master for any grid, so small updates are carried by the right fraction
+// of elements. Deterministic (no RNG state), same value in the copy and in the transpose.
+__device__ __forceinline__ float dither_bf16(float v, uint32_t idx) {
+  uint32_t h = idx * 2654435761u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  const uint32_t b = __float_as_uint(v);
+  if ((b & 0x7F800000u) == 0x7F800000u) return v;  // Inf / NaN pass through
+  return __uint_as_float((b + (h >> 16)) & 0xFFFF0000u);
+}
 // grid.x = total number of 64x64 tiles over all problems: every block finds its problem by a short scan.
 // block (32, 8): float2 loads / bf16x2 stores (128-byte warp rows both for the copy and for the transpose).
 __global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab, int n_problems) {
@@ -626,13 +642,14 @@ __global__ void repack_grouped_kernel(const RepackProblem* __restrict__ tab, int
     const int m = m0 + i, n = n0 + 2 * threadIdx.x;
     float v0 = 0.f, v1 = 0.f;
     if (m < pr.M) {
+      const uint32_t e = (uint32_t)pi * 0x9E3779B9u + (uint32_t)m * (uint32_t)pr.N + (uint32_t)n;
       if (even && n + 1 < pr.N) {
         const float2 v = *reinterpret_cast<const float2*>(pr.in + (size_t)m * pr.N + n);
-        v0 = v.x; v1 = v.y;
+        v0 = dither_bf16(v.x, e); v1 = dither_bf16(v.y, e + 1);   // exactly bf16-representable from here on
         if (pr.copy) *reinterpret_cast<uint32_t*>(pr.copy + (size_t)m * pr.N + n) = pack_bf16(v0, v1);
       } else {
-        if (n < pr.N) { v0 = pr.in[(size_t)m * pr.N + n]; if (pr.copy) pr.copy[(size_t)m * pr.N + n] = __float2bfloat16_rn(v0); }
-        if (n + 1 < pr.N) { v1 = pr.in[(size_t)m * pr.N + n + 1]; if (pr.copy) pr.copy[(size_t)m * pr.N + n + 1] = __float2bfloat16_rn(v1); }
+        if (n < pr.N) { v0 = dither_bf16(pr.in[(size_t)m * pr.N + n], e); if (pr.copy) pr.copy[(size_t)m * pr.N + n] = __float2bfloat16_rn(v0); }
+        if (n + 1 < pr.N) { v1 = dither_bf16(pr.in[(size_t)m * pr.N + n + 1], e + 1); if (pr.copy) pr.copy[(size_t)m * pr.N + n + 1] = __float2bfloat16_rn(v1); }
       }
     }
     tile[i][2 * threadIdx.x] = v0;

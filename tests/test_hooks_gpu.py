@@ -107,10 +107,11 @@ def test_single_block_forward_list_protocol():
         o3 = blocks[3]([x, deep, 2])
         assert o3[2] == 3
         xs = x.clone()
+        spliced = deep[2].half().float()[:, None, :]     # the reference splices `.half()` prompts (clip/model.py:327,344)
         if tower == "vis":
-            xs[T - n:] = deep[2][:, None, :]
+            xs[T - n:] = spliced
         else:
-            xs[1:1 + n] = deep[2][:, None, :]
+            xs[1:1 + n] = spliced
         o3b = blocks[3]([xs, [], 0])           # pre-spliced input, no prompts left: same result, counter untouched
         assert o3b[2] == 0 and torch.equal(o3[0], o3b[0])
         assert not torch.equal(o3[0], blocks[3]([x, [], 0])[0])

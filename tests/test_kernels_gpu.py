@@ -357,13 +357,42 @@ def test_grouped_small_linear_and_repack_match_single_calls():
     for pr, (y1, dW1, db1, dx1) in zip(probs, ref):   # same arithmetic and reduction order: bit-identical
         assert torch.equal(pr["y"], y1) and torch.equal(pr["dW"], dW1)
         assert torch.equal(pr["db"], db1) and torch.equal(pr["dx"], dx1)
-    # grouped repack == transpose_bf16 per matrix
-    ws = [rnd(96, 160, seed=70), rnd(512, 2048, seed=71), rnd(37, 51, seed=72)]
+    # grouped repack: bf16 copy + transposed copy of the fp32 masters with the fixed-threshold dithered rounding
+    # (see repack_grouped_kernel): copy and transpose hold the same values, every value is one of the two bf16
+    # neighbours of the master, bf16-representable masters pass unchanged, the rounding is unbiased on the fp16 grid
+    # (the reference's weights) where round-to-nearest-even is not, and it is deterministic
+    ws = [rnd(96, 160, seed=70), rnd(512, 2048, seed=71), rnd(37, 51, seed=72),
+          (rnd(512, 2048, seed=73) * 0.03).half().float(), rnd(64, 128, seed=74).to(BF16).float()]
     trip = [(w, torch.empty(w.shape[1], w.shape[0], device=DEV, dtype=BF16),
              torch.empty(w.shape, device=DEV, dtype=BF16)) for w in ws]
     ops.repack_grouped(*ops.repack_table(trip, DEV))
     for w, t, c in trip:
-        assert torch.equal(c, w.to(BF16)) and torch.equal(t, w.to(BF16).t().contiguous())
+        assert torch.equal(t, c.t().contiguous())
+        lo = (w.view(torch.int32) & -65536).view(torch.float32)             # truncation toward zero
+        hi = ((w.view(torch.int32) & -65536) + 65536).view(torch.float32)   # next bf16 away from zero
+        cf = c.float()
+        assert bool(((cf == lo) | (cf == hi)).all())
+        exact = lo == w
+        assert torch.equal(cf[exact], w[exact])
+    w, _, c = trip[3]
+    ulp = (w.abs().clamp_min(1e-30).log2().floor() - 7).exp2()
+    bias_dither = ((c.float() - w) / ulp).mean().item()
+    bias_rne = ((w.to(BF16).float() - w) / ulp).mean().item()
+    assert abs(bias_dither) < 2e-3, (bias_dither, bias_rne)
+    # a coherent update far below one ulp is carried, on average, at its true size (RNE from the fp16 grid gives ~1/16 ulp)
+    w2 = w + 0.01 * ulp
+    base = [(w, torch.empty(w.shape[1], w.shape[0], device=DEV, dtype=BF16), torch.empty(w.shape, device=DEV, dtype=BF16))]
+    ops.repack_grouped(*ops.repack_table(base, DEV))      # same problem slot (= same thresholds) as the updated copy
+    c = base[0][2]
+    trip2 = [(w2, torch.empty(w2.shape[1], w2.shape[0], device=DEV, dtype=BF16), torch.empty(w2.shape, device=DEV, dtype=BF16))]
+    ops.repack_grouped(*ops.repack_table(trip2, DEV))
+    moved = ((trip2[0][2].float() - c.float()) / ulp).mean().item()
+    moved_rne = ((w2.to(BF16).float() - w.to(BF16).float()) / ulp).mean().item()
+    print(f"repack of fp16-grid weights after a +0.01 ulp update: dithered copy moves {moved:.4f} ulp on average, RNE {moved_rne:.4f}")
+    assert abs(moved - 0.01) < 4e-3 and moved_rne > 0.03
+    again = [(w2, torch.empty_like(trip2[0][1]), torch.empty_like(trip2[0][2]))]
+    ops.repack_grouped(*ops.repack_table(again, DEV))
+    assert torch.equal(again[0][2], trip2[0][2])
 
 
 @pytest.mark.parametrize("B,C", [(4, 10), (32, 38), (32, 1000)])
