@@ -42,6 +42,7 @@ SIGNATURES = {
     "mfk_prompt_splice_bwd": [P, P, P, I, I, I, I, I, I, I, P],
     "mfk_prompt_splice_bwd_batched": [P, L, P, L, I, I, I, I, I, I, I, P],
     "mfk_scatter_rows": [P, P, P, P, I, I, P],
+    "mfk_scatter_rows_dense": [P, P, P, I, I, I, P],
     "mfk_gather_rows": [P, P, P, I, L, I, P],
     "mfk_transpose_bf16": [P, I, L, P, L, P, L, I, I, P],
     "mfk_cast_f32_bf16": [P, P, L, P],

@@ -383,6 +383,20 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dx, const int* __r
   }
 }
 
+// Dense form: g[m, :] = dx[n, :] if m == rowidx[n] (n = m / T: exactly one consumed row per sequence) else 0, for ALL
+// N*T rows in one pass of float4 stores — replaces two full-buffer fills + the sparse scatter at the last block.
+__global__ void scatter_rows_dense_kernel(const float4* __restrict__ dx, const int* __restrict__ rowidx,
+                                          float4* __restrict__ g, int rows, int T, int D4) {
+  pdl_trigger();
+  pdl_wait();
+  for (int m = blockIdx.x; m < rows; m += gridDim.x) {
+    const int n = m / T;
+    const bool hit = rowidx[n] == m;
+    for (int i = threadIdx.x; i < D4; i += blockDim.x)
+      g[(size_t)m * D4 + i] = hit ? dx[(size_t)n * D4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // dst[r, :] = src[rowidx[r], :] in 16-byte chunks (row_bytes % 16 == 0)
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ rowidx,
                                    uint4* __restrict__ dst, int chunks_per_row) {
@@ -876,6 +890,17 @@ extern "C" int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, vo
                                 void* stream) {
   if (!dx || !rowidx || !g || R <= 0) return MFK_EARG;
   launch_pdl(scatter_rows_kernel, dim3(R), dim3(128), 0, ST(stream), dx, rowidx, g, static_cast<bf16*>(g_bf16), D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_scatter_rows_dense(const float* dx, const int* rowidx, float* g, int N, int T, int D, void* stream) {
+  if (!dx || !rowidx || !g || N <= 0 || T <= 0 || D <= 0 || D % 4) return MFK_EARG;
+  if ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(g)) & 15) return MFK_EALIGN;
+  const int rows = N * T, D4 = D / 4;
+  const int threads = D4 >= 192 ? 192 : (D4 >= 128 ? 128 : 64);
+  launch_pdl(scatter_rows_dense_kernel, dim3(rows < 148 * 8 ? rows : 148 * 8), dim3(threads), 0, ST(stream),
+             reinterpret_cast<const float4*>(dx), rowidx, reinterpret_cast<float4*>(g), rows, T, D4);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

@@ -19,19 +19,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;
 }
 
-// rows [0,B) = image features, rows [B,B+C) = text features
+// rows [0,B) = image features, rows [B,B+C) = text features; warp per row, lane-strided accumulation: the same
+// arithmetic order as phase 1 of head_fused_kernel, so inference logits equal the training step's bit for bit
 __global__ void head_normalize_kernel(const float* __restrict__ fi, const float* __restrict__ ft, float* __restrict__ a,
                                       float* __restrict__ t, float* __restrict__ ni, float* __restrict__ nt, int B,
                                       int C, int E) {
-  __shared__ float red[8];
-  const int r = blockIdx.x;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= B + C) return;
   const float* src = r < B ? fi + (size_t)r * E : ft + (size_t)(r - B) * E;
   float* dst = r < B ? a + (size_t)r * E : t + (size_t)(r - B) * E;
   float q = 0.f;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) q += src[i] * src[i];
-  const float nrm = fmaxf(sqrtf(block_sum(q, red)), 1e-8f);
-  for (int i = threadIdx.x; i < E; i += blockDim.x) dst[i] = src[i] / nrm;
-  if (threadIdx.x == 0) (r < B ? ni[r] : nt[r - B]) = nrm;
+  for (int i = lane; i < E; i += 32) q += src[i] * src[i];
+  const float nrm = fmaxf(sqrtf(warp_sum(q)), 1e-8f);
+  for (int i = lane; i < E; i += 32) dst[i] = src[i] / nrm;
+  if (lane == 0) (r < B ? ni[r] : nt[r - B]) = nrm;
 }
 
 __global__ void head_logits_kernel(const float* __restrict__ a, const float* __restrict__ t,
@@ -150,6 +151,146 @@ __global__ void head_grad_txt_kernel(const float* __restrict__ dlog, const long 
     dft[(size_t)c * E + i] = (dt[i] - t[(size_t)c * E + i] * proj) / nt[c];
 }
 
+
+// ---- the whole training head in ONE launch (north_star: "a single fused kernel computes the L2-normalised logits plus
+// cross-entropy and its gradient"): one CTA of 1024 threads, a / t / dlogits resident in shared memory. The head joins
+// the two towers, so its launches sit on the critical path of the step; the work itself is ~0.5 MFLOP.
+//   phase 1  warp per row     : norms, a = img / |img|, t = txt / |txt|                      (rows strided over warps)
+//   phase 2  warp per (b, c)  : logits = s * a_b . t_c
+//   phase 3  warp per b       : log-sum-exp, dlogits, cos(a_b, t_y), per-row loss term
+//   phase 4  thread 0         : loss = sum_b loss_b (batch order)
+//   phase 5  warp per b       : d img_b = normalize' (s * dlog_b t + alignment)              (sum over c in class order)
+//            warp per c       : d txt_c = normalize' (s * dlog^T_c a + alignment)            (sum over b in batch order)
+// Every reduction has a fixed order; results do not depend on the launch configuration.
+constexpr int HEAD_FUSED_THREADS = 1024;
+template <int EPL>  // E / 32 elements per lane
+__global__ void __launch_bounds__(HEAD_FUSED_THREADS, 1)
+head_fused_kernel(const float* __restrict__ fi, const float* __restrict__ ft, const float* __restrict__ logit_scale,
+                  const long long* __restrict__ label, float* __restrict__ logits, float* __restrict__ loss,
+                  float* __restrict__ dfi, float* __restrict__ dft, int B, int C) {
+  constexpr int E = EPL * 32;
+  extern __shared__ float hs[];
+  float* a = hs;                          // [B, E]
+  float* t = a + (size_t)B * E;           // [C, E]
+  float* dlog = t + (size_t)C * E;        // [B, C]
+  float* lg = dlog + (size_t)B * C;       // [B, C]
+  float* ni = lg + (size_t)B * C;         // [B]
+  float* nt = ni + B;                     // [C]
+  float* cosb = nt + C;                   // [B]
+  float* na2 = cosb + B;                  // [B]
+  float* nt2 = na2 + B;                   // [B]
+  float* loss_b = nt2 + B;                // [B]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = HEAD_FUSED_THREADS / 32;
+  const float s = fminf(expf(logit_scale[0]), 100.f);
+  pdl_trigger();
+  pdl_wait();
+  for (int r = warp; r < B + C; r += nw) {
+    const float* src = r < B ? fi + (size_t)r * E : ft + (size_t)(r - B) * E;
+    float* dst = r < B ? a + (size_t)r * E : t + (size_t)(r - B) * E;
+    float v[EPL], q = 0.f;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) { v[j] = src[lane + 32 * j]; q += v[j] * v[j]; }
+    const float nrm = fmaxf(sqrtf(warp_sum(q)), 1e-8f);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) dst[lane + 32 * j] = v[j] / nrm;
+    if (lane == 0) (r < B ? ni[r] : nt[r - B]) = nrm;
+  }
+  __syncthreads();
+  for (int w = warp; w < B * C; w += nw) {
+    const int b = w / C, c = w % C;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) acc += a[(size_t)b * E + lane + 32 * j] * t[(size_t)c * E + lane + 32 * j];
+    acc = warp_sum(acc);
+    if (lane == 0) { lg[w] = s * acc; logits[w] = s * acc; }
+  }
+  __syncthreads();
+  for (int b = warp; b < B; b += nw) {
+    const int y = (int)label[b];
+    const float* row = lg + (size_t)b * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(row[c] - mx);
+    const float lse = mx + logf(warp_sum(se));
+    for (int c = lane; c < C; c += 32) dlog[(size_t)b * C + c] = (expf(row[c] - lse) - (c == y ? 1.f : 0.f)) / (float)B;
+    float dot = 0.f, qa = 0.f, qt = 0.f;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const float av = a[(size_t)b * E + lane + 32 * j], tv = t[(size_t)y * E + lane + 32 * j];
+      dot += av * tv; qa += av * av; qt += tv * tv;
+    }
+    dot = warp_sum(dot); qa = warp_sum(qa); qt = warp_sum(qt);
+    if (lane == 0) {
+      const float n_a = fmaxf(sqrtf(qa), 1e-8f), n_t = fmaxf(sqrtf(qt), 1e-8f);
+      const float cs = dot / (n_a * n_t);
+      cosb[b] = cs; na2[b] = n_a; nt2[b] = n_t;
+      loss_b[b] = (lse - row[y]) / (float)B + 0.5f * (1.f - cs) / (float)B;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int b = 0; b < B; ++b) tot += loss_b[b];
+    loss[0] = tot;
+  }
+  const float dcos = -0.5f / (float)B;
+  for (int r = warp; r < B + C; r += nw) {
+    float d[EPL], proj = 0.f;
+    if (r < B) {
+      const int b = r, y = (int)label[b];
+      const float cs = cosb[b], n_a = na2[b], n_t = nt2[b];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) d[j] = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float w = dlog[(size_t)b * C + c];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) d[j] += w * t[(size_t)c * E + lane + 32 * j];
+      }
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const float av = a[(size_t)b * E + lane + 32 * j];
+        d[j] = s * d[j] + dcos * (t[(size_t)y * E + lane + 32 * j] / (n_a * n_t) - cs * av / (n_a * n_a));
+        proj += av * d[j];
+      }
+      proj = warp_sum(proj);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        dfi[(size_t)b * E + lane + 32 * j] = (d[j] - a[(size_t)b * E + lane + 32 * j] * proj) / ni[b];
+    } else {
+      const int c = r - B;
+      float al[EPL];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) { d[j] = 0.f; al[j] = 0.f; }
+      for (int b = 0; b < B; ++b) {
+        const float w = dlog[(size_t)b * C + c];
+        const bool mine = (int)label[b] == c;
+        const float n_a = na2[b], n_t = nt2[b], cs = cosb[b];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const float av = a[(size_t)b * E + lane + 32 * j];
+          d[j] += w * av;
+          if (mine) al[j] += dcos * (av / (n_a * n_t) - cs * t[(size_t)c * E + lane + 32 * j] / (n_t * n_t));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        d[j] = s * d[j] + al[j];
+        proj += t[(size_t)c * E + lane + 32 * j] * d[j];
+      }
+      proj = warp_sum(proj);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        dft[(size_t)c * E + lane + 32 * j] = (d[j] - t[(size_t)c * E + lane + 32 * j] * proj) / nt[c];
+    }
+  }
+}
+
+static size_t head_fused_smem(int B, int C, int E) {
+  return sizeof(float) * ((size_t)(B + C) * E + 2 * (size_t)B * C + 5 * (size_t)B + C);
+}
+
 }  // namespace
 
 #define ST(s) static_cast<cudaStream_t>(s)
@@ -165,6 +306,26 @@ extern "C" int mfk_head_forward_backward(const float* img_feat, const float* txt
   if (!img_feat || !txt_feat || !logit_scale || !logits || !ws || B <= 0 || C <= 0 || E <= 0) return MFK_EARG;
   const bool train = label != nullptr;
   if (train && (!loss || !d_img || !d_txt)) return MFK_EARG;
+  // training head: one launch when the normalised features fit one CTA's shared memory (every BASELINE training
+  // shape: B <= 64 with C <= 38); the multi-kernel path below serves inference (logits only) and larger heads
+  if (train && E == 512 && head_fused_smem(B, C, E) <= 227u * 1024u) {
+    const size_t smem = head_fused_smem(B, C, E);
+    auto launch = [&](auto kern) -> int {
+      static int attr_done = 0;  // one attribute per instantiation; idempotent, so a race only repeats the call
+      if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+          return (int)cudaGetLastError();
+        attr_done = 1;
+      }
+      kern<<<1, HEAD_FUSED_THREADS, smem, ST(stream)>>>(img_feat, txt_feat, logit_scale, label, logits, loss, d_img,
+                                                         d_txt, B, C);
+      return MFK_OK;
+    };
+    const int rc = launch(head_fused_kernel<16>);
+    if (rc != MFK_OK) return rc;
+    MFK_CHECK_LAUNCH();
+    return MFK_OK;
+  }
   float* a = ws;
   float* t = a + (size_t)B * E;
   float* ni = t + (size_t)C * E;
@@ -174,7 +335,7 @@ extern "C" int mfk_head_forward_backward(const float* img_feat, const float* txt
   float* cosb = loss_b + B;
   float* na2 = cosb + B;
   float* nt2 = na2 + B;
-  head_normalize_kernel<<<B + C, 128, 0, ST(stream)>>>(img_feat, txt_feat, a, t, ni, nt, B, C, E);
+  head_normalize_kernel<<<(B + C + 3) / 4, 128, 0, ST(stream)>>>(img_feat, txt_feat, a, t, ni, nt, B, C, E);
   const long long warps = (long long)B * C;
   head_logits_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ST(stream)>>>(a, t, logit_scale, logits, B, C, E);
   if (train) {

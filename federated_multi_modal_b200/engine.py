@@ -415,8 +415,9 @@ class MapleEngine:
         if wg:
             ops.gemm_at_b(g16, ws["att_r"], G[pre + "attn.out_proj.weight"])
             ops.colsum(g, G[pre + "attn.out_proj.bias"], ws["csum"])
-        ws["g"].zero_(); ws["g16"].zero_()
-        ops.scatter_rows(g, rows, ws["g"], ws["g16"])
+        # dense scatter: every row of ws["g"] is written (zeros except the consumed rows) in one pass; ws["g16"] is an
+        # OUTPUT of the following ln_1 backward, so it needs neither the fill nor the scatter
+        ops.scatter_rows_dense(g, rows, ws["g"], tw.N, tw.T)
         tw.last_rows = rows  # ws["dh_r"] (gradient wrt the attention output rows) feeds the single-query backward
 
     def _block_bwd(self, tw: _Tower, l: int, attn_only: bool = False, splice_grad=None):
@@ -568,7 +569,7 @@ class MapleEngine:
         """Text features of the evaluation path. They are input independent and cached across batches, so they are
         computed in the split-operand fp32 mode at no per-batch cost: with bf16 operands the 10-token text tower
         contributes ~3x the logit error of the 199-token vision tower (relative feature error 9e-3 against 3e-3,
-        measured with the bf16-emulating oracle), which is most of the distance to the reference's logits.
+        measured on the CPU with bf16-rounded operands), which is most of the distance to the reference's logits.
         MFK_EVAL_TEXT=bf16 keeps the bf16 tensor-core tower (the training step always uses it)."""
         if self.eval_text_f32:
             return self._text_features_f32(class_range)

@@ -160,6 +160,13 @@ def scatter_rows(dx, rowidx, g, g_bf16):
     call("mfk_scatter_rows", dx, rowidx, g, g_bf16, dx.shape[0], dx.shape[1], stream_ptr())
 
 
+def scatter_rows_dense(dx, rowidx, g, N, T):
+    """g[N*T, D] = zeros except g[rowidx[n]] = dx[n] (one consumed row per sequence); no prior zero fill needed."""
+    _chk(dx, F32, "dx"); _chk(g, F32, "g")
+    assert g.shape[0] == N * T and dx.shape[0] == N and rowidx.dtype == torch.int32
+    call("mfk_scatter_rows_dense", dx, rowidx, g, N, T, dx.shape[1], stream_ptr())
+
+
 def gather_rows(src, rowidx, dst, scatter=False):
     """dst[r] = src[rowidx[r]] (or the inverse scatter into a pre-zeroed dst); rows of equal byte length."""
     call("mfk_gather_rows", src, rowidx, dst, rowidx.numel(), src.shape[-1] * src.element_size(), int(scatter),
@@ -267,8 +274,10 @@ def head_workspace_floats(B, C, E) -> int:
 def head_forward_backward(img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws):
     B, E = img_feat.shape
     C = txt_feat.shape[0]
+    # training: ONE fused launch when a / t / dlogits fit one CTA's shared memory (mfk_head.cu), else six kernels
+    fused = label is not None and E == 512 and 4 * ((B + C) * E + 2 * B * C + 5 * B + C) <= 227 * 1024
     call("mfk_head_forward_backward", img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws, B, C, E,
-         stream_ptr(), kernels=2 if label is None else 6)
+         stream_ptr(), kernels=2 if label is None else (1 if fused else 6))
 
 
 def fedavg_reduce(ptrs_dev, weights_dev, divisor, K, n, in_is_fp16, out_f32, out_f16, flags_dev):

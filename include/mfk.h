@@ -135,6 +135,9 @@ int mfk_prompt_splice_bwd(float* g, void* g_bf16, float* dprompt, int N, int T, 
 int mfk_prompt_splice_bwd_batched(float* g, long long g_stride, float* dprompt, long long dp_stride, int layers,
                                   int N, int T, int row0, int n_ctx, int D, int round_fp16, void* stream);
 int mfk_scatter_rows(const float* dx, const int* rowidx, float* g, void* g_bf16, int R, int D, void* stream);
+/* Dense form for the last block's backward (one consumed row per sequence, rowidx[n] in [n*T, (n+1)*T)): writes ALL
+ * N*T rows of g — dx[n,:] at row rowidx[n], zeros elsewhere — in one pass, so g needs no zero fill beforehand. */
+int mfk_scatter_rows_dense(const float* dx, const int* rowidx, float* g, int N, int T, int D, void* stream);
 /* scatter == 0: dst[r,:] = src[rowidx[r],:]; scatter != 0: dst[rowidx[r],:] = src[r,:] (dst pre-zeroed). Rows are
  * row_bytes long (multiple of 16). Only the CLS row (clip/model.py:567) / EOT row (trainers/maple.py:76) of the
  * last block's output is consumed, so that block's out-proj + MLP run on the gathered rows only.       */

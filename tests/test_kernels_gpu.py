@@ -395,7 +395,7 @@ def test_grouped_small_linear_and_repack_match_single_calls():
     assert torch.equal(again[0][2], trip2[0][2])
 
 
-@pytest.mark.parametrize("B,C", [(4, 10), (32, 38), (32, 1000)])
+@pytest.mark.parametrize("B,C", [(4, 10), (32, 10), (64, 21), (32, 38), (32, 1000)])  # last one: multi-kernel path
 def test_head(B, C):
     E = 512
     fi = rnd(B, E, seed=40).requires_grad_(True)
