@@ -153,16 +153,28 @@ __global__ void head_grad_txt_kernel(const float* __restrict__ dlog, const long 
 
 
 // ---- the whole training head in ONE launch (north_star: "a single fused kernel computes the L2-normalised logits plus
-// cross-entropy and its gradient"): one CTA of 1024 threads, a / t / dlogits resident in shared memory. The head joins
-// the two towers, so its launches sit on the critical path of the step; the work itself is ~0.5 MFLOP.
-//   phase 1  warp per row     : norms, a = img / |img|, t = txt / |txt|                      (rows strided over warps)
-//   phase 2  warp per (b, c)  : logits = s * a_b . t_c
-//   phase 3  warp per b       : log-sum-exp, dlogits, cos(a_b, t_y), per-row loss term
-//   phase 4  thread 0         : loss = sum_b loss_b (batch order)
-//   phase 5  warp per b       : d img_b = normalize' (s * dlog_b t + alignment)              (sum over c in class order)
-//            warp per c       : d txt_c = normalize' (s * dlog^T_c a + alignment)            (sum over b in batch order)
-// Every reduction has a fixed order; results do not depend on the launch configuration.
-constexpr int HEAD_FUSED_THREADS = 1024;
+// cross-entropy and its gradient"): one thread-block CLUSTER of 8 CTAs, everything resident in (distributed) shared
+// memory. The head joins the two towers, so its launches sit on the critical path of the step; one CTA alone is
+// issue-bound at ~45 us for B=32, C=10 (measured), the six-kernel form pays five launch boundaries.
+//   CTA r owns the images b = r, r+8, ... and the classes c = r, r+8, ...
+//   phase 1  warp per row : t = txt / |txt| for ALL classes (redundant, C is small), a = img / |img| for own images
+//   phase 2  warp per (b, c) of own images: logits = s * a_b . t_c
+//   phase 3  warp per own image: log-sum-exp, dlogits row, cos(a_b, t_y), loss term -> loss_b is pushed to CTA 0
+//   phase 4  warp per own image: d img_b  (complete: needs only the own dlogits row and t)
+//            warp per class     : PARTIAL d txt over the own images (class order independent of the cluster layout)
+//   -- cluster barrier --
+//   phase 5  CTA 0: loss = sum_b loss_b (batch order); warp per own class: d txt_c = normalize'(sum of the 8 partials
+//            read through DSMEM in CTA order)
+// Every reduction has a fixed order; logits use the arithmetic of the multi-kernel inference path bit for bit.
+constexpr int HEAD_CLUSTER = 8, HEAD_FUSED_THREADS = 512;
+__device__ __forceinline__ float ld_dsmem(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_dsmem(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
 template <int EPL>  // E / 32 elements per lane
 __global__ void __launch_bounds__(HEAD_FUSED_THREADS, 1)
 head_fused_kernel(const float* __restrict__ fi, const float* __restrict__ ft, const float* __restrict__ logit_scale,
@@ -170,125 +182,147 @@ head_fused_kernel(const float* __restrict__ fi, const float* __restrict__ ft, co
                   float* __restrict__ dfi, float* __restrict__ dft, int B, int C) {
   constexpr int E = EPL * 32;
   extern __shared__ float hs[];
-  float* a = hs;                          // [B, E]
-  float* t = a + (size_t)B * E;           // [C, E]
-  float* dlog = t + (size_t)C * E;        // [B, C]
-  float* lg = dlog + (size_t)B * C;       // [B, C]
-  float* ni = lg + (size_t)B * C;         // [B]
-  float* nt = ni + B;                     // [C]
-  float* cosb = nt + C;                   // [B]
-  float* na2 = cosb + B;                  // [B]
-  float* nt2 = na2 + B;                   // [B]
-  float* loss_b = nt2 + B;                // [B]
+  const int rank = (int)cluster_ctarank();
+  const int nb = (B - rank + HEAD_CLUSTER - 1) / HEAD_CLUSTER;   // own images: b = rank + 8 * i
+  const int nbmax = (B + HEAD_CLUSTER - 1) / HEAD_CLUSTER;       // same layout in every CTA (DSMEM offsets)
+  float* t = hs;                              // [C, E]      all classes
+  float* part = t + (size_t)C * E;            // [C, E]      partial d txt over the own images
+  float* a = part + (size_t)C * E;            // [nbmax, E]  own images
+  float* dlog = a + (size_t)nbmax * E;        // [nbmax, C]
+  float* lg = dlog + (size_t)nbmax * C;       // [nbmax, C]
+  float* ni = lg + (size_t)nbmax * C;         // [nbmax]
+  float* cosb = ni + nbmax;                   // [nbmax]
+  float* na2 = cosb + nbmax;                  // [nbmax]
+  float* nt2 = na2 + nbmax;                   // [nbmax]
+  float* nt = nt2 + nbmax;                    // [C]
+  float* loss_b = nt + C;                     // [B]  (complete in CTA 0 only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = HEAD_FUSED_THREADS / 32;
   const float s = fminf(expf(logit_scale[0]), 100.f);
   pdl_trigger();
   pdl_wait();
-  for (int r = warp; r < B + C; r += nw) {
-    const float* src = r < B ? fi + (size_t)r * E : ft + (size_t)(r - B) * E;
-    float* dst = r < B ? a + (size_t)r * E : t + (size_t)(r - B) * E;
+  for (int r = warp; r < nb + C; r += nw) {
+    const float* src = r < nb ? fi + (size_t)(rank + HEAD_CLUSTER * r) * E : ft + (size_t)(r - nb) * E;
+    float* dst = r < nb ? a + (size_t)r * E : t + (size_t)(r - nb) * E;
     float v[EPL], q = 0.f;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) { v[j] = src[lane + 32 * j]; q += v[j] * v[j]; }
     const float nrm = fmaxf(sqrtf(warp_sum(q)), 1e-8f);
 #pragma unroll
     for (int j = 0; j < EPL; ++j) dst[lane + 32 * j] = v[j] / nrm;
-    if (lane == 0) (r < B ? ni[r] : nt[r - B]) = nrm;
+    if (lane == 0) (r < nb ? ni[r] : nt[r - nb]) = nrm;
   }
   __syncthreads();
-  for (int w = warp; w < B * C; w += nw) {
-    const int b = w / C, c = w % C;
+  for (int w = warp; w < nb * C; w += nw) {
+    const int i = w / C, c = w % C;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) acc += a[(size_t)b * E + lane + 32 * j] * t[(size_t)c * E + lane + 32 * j];
+    for (int j = 0; j < EPL; ++j) acc += a[(size_t)i * E + lane + 32 * j] * t[(size_t)c * E + lane + 32 * j];
     acc = warp_sum(acc);
-    if (lane == 0) { lg[w] = s * acc; logits[w] = s * acc; }
+    if (lane == 0) { lg[w] = s * acc; logits[(size_t)(rank + HEAD_CLUSTER * i) * C + c] = s * acc; }
   }
-  __syncthreads();
-  for (int b = warp; b < B; b += nw) {
-    const int y = (int)label[b];
-    const float* row = lg + (size_t)b * C;
+  cluster_sync_all();  // every CTA of the cluster is running: its shared memory may be written remotely from here on
+  const uint32_t loss0 = map_to_cta(smem_u32(loss_b), 0);
+  for (int i = warp; i < nb; i += nw) {
+    const int b = rank + HEAD_CLUSTER * i, y = (int)label[b];
+    const float* row = lg + (size_t)i * C;
     float mx = -INFINITY;
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
     mx = warp_max(mx);
     float se = 0.f;
     for (int c = lane; c < C; c += 32) se += expf(row[c] - mx);
     const float lse = mx + logf(warp_sum(se));
-    for (int c = lane; c < C; c += 32) dlog[(size_t)b * C + c] = (expf(row[c] - lse) - (c == y ? 1.f : 0.f)) / (float)B;
+    for (int c = lane; c < C; c += 32) dlog[(size_t)i * C + c] = (expf(row[c] - lse) - (c == y ? 1.f : 0.f)) / (float)B;
     float dot = 0.f, qa = 0.f, qt = 0.f;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-      const float av = a[(size_t)b * E + lane + 32 * j], tv = t[(size_t)y * E + lane + 32 * j];
+      const float av = a[(size_t)i * E + lane + 32 * j], tv = t[(size_t)y * E + lane + 32 * j];
       dot += av * tv; qa += av * av; qt += tv * tv;
     }
     dot = warp_sum(dot); qa = warp_sum(qa); qt = warp_sum(qt);
     if (lane == 0) {
       const float n_a = fmaxf(sqrtf(qa), 1e-8f), n_t = fmaxf(sqrtf(qt), 1e-8f);
       const float cs = dot / (n_a * n_t);
-      cosb[b] = cs; na2[b] = n_a; nt2[b] = n_t;
-      loss_b[b] = (lse - row[y]) / (float)B + 0.5f * (1.f - cs) / (float)B;
+      cosb[i] = cs; na2[i] = n_a; nt2[i] = n_t;
+      st_dsmem(loss0 + 4u * (uint32_t)b, (lse - row[y]) / (float)B + 0.5f * (1.f - cs) / (float)B);
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  const float dcos = -0.5f / (float)B;
+  for (int r = warp; r < nb + C; r += nw) {
+    float d[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) d[j] = 0.f;
+    if (r < nb) {
+      const int i = r, b = rank + HEAD_CLUSTER * i, y = (int)label[b];
+      const float cs = cosb[i], n_a = na2[i], n_t = nt2[i];
+      for (int c = 0; c < C; ++c) {
+        const float w = dlog[(size_t)i * C + c];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) d[j] += w * t[(size_t)c * E + lane + 32 * j];
+      }
+      float proj = 0.f;
+      const float r1 = 1.f / (n_a * n_t), r2 = cs / (n_a * n_a);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const float av = a[(size_t)i * E + lane + 32 * j];
+        d[j] = s * d[j] + dcos * (t[(size_t)y * E + lane + 32 * j] * r1 - av * r2);
+        proj += av * d[j];
+      }
+      proj = warp_sum(proj);
+      const float rn = 1.f / ni[i];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        dfi[(size_t)b * E + lane + 32 * j] = (d[j] - a[(size_t)i * E + lane + 32 * j] * proj) * rn;
+    } else {
+      const int c = r - nb;
+      float al[EPL];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) al[j] = 0.f;
+      for (int i = 0; i < nb; ++i) {
+        const float w = dlog[(size_t)i * C + c];
+        const bool mine = (int)label[rank + HEAD_CLUSTER * i] == c;
+        const float r1 = 1.f / (na2[i] * nt2[i]), r2 = cosb[i] / (nt2[i] * nt2[i]);
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const float av = a[(size_t)i * E + lane + 32 * j];
+          d[j] += w * av;
+          if (mine) al[j] += dcos * (av * r1 - t[(size_t)c * E + lane + 32 * j] * r2);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) part[(size_t)c * E + lane + 32 * j] = s * d[j] + al[j];
+    }
+  }
+  cluster_sync_all();  // partials and loss terms of every CTA are in place (release / acquire at cluster scope)
+  if (rank == 0 && threadIdx.x == 0) {
     float tot = 0.f;
     for (int b = 0; b < B; ++b) tot += loss_b[b];
     loss[0] = tot;
   }
-  const float dcos = -0.5f / (float)B;
-  for (int r = warp; r < B + C; r += nw) {
+  const uint32_t part_local = smem_u32(part);
+  for (int c = rank + HEAD_CLUSTER * warp; c < C; c += HEAD_CLUSTER * nw) {
     float d[EPL], proj = 0.f;
-    if (r < B) {
-      const int b = r, y = (int)label[b];
-      const float cs = cosb[b], n_a = na2[b], n_t = nt2[b];
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) d[j] = 0.f;
-      for (int c = 0; c < C; ++c) {
-        const float w = dlog[(size_t)b * C + c];
+    for (int j = 0; j < EPL; ++j) d[j] = 0.f;
+    for (int k = 0; k < HEAD_CLUSTER; ++k) {   // CTA order == fixed summation order
+      const uint32_t base = map_to_cta(part_local, (uint32_t)k) + 4u * (uint32_t)((size_t)c * E + lane);
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) d[j] += w * t[(size_t)c * E + lane + 32 * j];
-      }
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        const float av = a[(size_t)b * E + lane + 32 * j];
-        d[j] = s * d[j] + dcos * (t[(size_t)y * E + lane + 32 * j] / (n_a * n_t) - cs * av / (n_a * n_a));
-        proj += av * d[j];
-      }
-      proj = warp_sum(proj);
-#pragma unroll
-      for (int j = 0; j < EPL; ++j)
-        dfi[(size_t)b * E + lane + 32 * j] = (d[j] - a[(size_t)b * E + lane + 32 * j] * proj) / ni[b];
-    } else {
-      const int c = r - B;
-      float al[EPL];
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) { d[j] = 0.f; al[j] = 0.f; }
-      for (int b = 0; b < B; ++b) {
-        const float w = dlog[(size_t)b * C + c];
-        const bool mine = (int)label[b] == c;
-        const float n_a = na2[b], n_t = nt2[b], cs = cosb[b];
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-          const float av = a[(size_t)b * E + lane + 32 * j];
-          d[j] += w * av;
-          if (mine) al[j] += dcos * (av / (n_a * n_t) - cs * t[(size_t)c * E + lane + 32 * j] / (n_t * n_t));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        d[j] = s * d[j] + al[j];
-        proj += t[(size_t)c * E + lane + 32 * j] * d[j];
-      }
-      proj = warp_sum(proj);
-#pragma unroll
-      for (int j = 0; j < EPL; ++j)
-        dft[(size_t)c * E + lane + 32 * j] = (d[j] - t[(size_t)c * E + lane + 32 * j] * proj) / nt[c];
+      for (int j = 0; j < EPL; ++j) d[j] += ld_dsmem(base + 128u * (uint32_t)j);
     }
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) proj += t[(size_t)c * E + lane + 32 * j] * d[j];
+    proj = warp_sum(proj);
+    const float rn = 1.f / nt[c];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      dft[(size_t)c * E + lane + 32 * j] = (d[j] - t[(size_t)c * E + lane + 32 * j] * proj) * rn;
   }
+  cluster_sync_all();  // no CTA may exit while a peer still reads its shared memory
 }
 
 static size_t head_fused_smem(int B, int C, int E) {
-  return sizeof(float) * ((size_t)(B + C) * E + 2 * (size_t)B * C + 5 * (size_t)B + C);
+  const size_t nbmax = (size_t)(B + HEAD_CLUSTER - 1) / HEAD_CLUSTER;
+  return sizeof(float) * (2 * (size_t)C * E + nbmax * E + 2 * nbmax * C + 4 * nbmax + C + B);
 }
 
 }  // namespace
@@ -306,20 +340,21 @@ extern "C" int mfk_head_forward_backward(const float* img_feat, const float* txt
   if (!img_feat || !txt_feat || !logit_scale || !logits || !ws || B <= 0 || C <= 0 || E <= 0) return MFK_EARG;
   const bool train = label != nullptr;
   if (train && (!loss || !d_img || !d_txt)) return MFK_EARG;
-  // training head: one launch when the normalised features fit one CTA's shared memory (every BASELINE training
+  // training head: one launch when the normalised features fit the cluster's shared memory (every BASELINE training
   // shape: B <= 64 with C <= 38); the multi-kernel path below serves inference (logits only) and larger heads
   if (train && E == 512 && head_fused_smem(B, C, E) <= 227u * 1024u) {
     const size_t smem = head_fused_smem(B, C, E);
     auto launch = [&](auto kern) -> int {
-      static int attr_done = 0;  // one attribute per instantiation; idempotent, so a race only repeats the call
+      static int attr_done = 0;  // idempotent, so a race only repeats the call
       if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
           return (int)cudaGetLastError();
         attr_done = 1;
       }
-      kern<<<1, HEAD_FUSED_THREADS, smem, ST(stream)>>>(img_feat, txt_feat, logit_scale, label, logits, loss, d_img,
-                                                         d_txt, B, C);
-      return MFK_OK;
+      const cudaError_t e = launch_pdl_cluster(kern, dim3(HEAD_CLUSTER), dim3(HEAD_FUSED_THREADS), smem, ST(stream),
+                                               HEAD_CLUSTER, img_feat, txt_feat, logit_scale, label, logits, loss,
+                                               d_img, d_txt, B, C);
+      return e == cudaSuccess ? MFK_OK : (int)e;
     };
     const int rc = launch(head_fused_kernel<16>);
     if (rc != MFK_OK) return rc;

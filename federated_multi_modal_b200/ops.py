@@ -274,8 +274,9 @@ def head_workspace_floats(B, C, E) -> int:
 def head_forward_backward(img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws):
     B, E = img_feat.shape
     C = txt_feat.shape[0]
-    # training: ONE fused launch when a / t / dlogits fit one CTA's shared memory (mfk_head.cu), else six kernels
-    fused = label is not None and E == 512 and 4 * ((B + C) * E + 2 * B * C + 5 * B + C) <= 227 * 1024
+    # training: ONE fused launch (8-CTA cluster) when the features fit its shared memory (mfk_head.cu), else six kernels
+    nb = (B + 7) // 8
+    fused = label is not None and E == 512 and 4 * (2 * C * E + nb * E + 2 * nb * C + 4 * nb + C + B) <= 227 * 1024
     call("mfk_head_forward_backward", img_feat, txt_feat, logit_scale, label, logits, loss, d_img, d_txt, ws, B, C, E,
          stream_ptr(), kernels=2 if label is None else (1 if fused else 6))
 

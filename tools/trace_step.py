@@ -28,7 +28,24 @@ for e in ev:
     agg[name][1] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
     tr = e.time_range
     tmin, tmax = min(tmin, tr.start), max(tmax, tr.end)
+# per-stream occupancy: union of kernel intervals vs the step span (idle = launch gaps / dependencies)
+by_stream = collections.defaultdict(list)
+for e in ev:
+    by_stream[getattr(e, "device_index", 0), getattr(e, "stream", None) or getattr(e, "device_resource_id", 0)].append(
+        (e.time_range.start, e.time_range.end))
+for k, iv in sorted(by_stream.items(), key=lambda kv: -len(kv[1])):
+    iv.sort()
+    busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+    for a, b_ in iv[1:]:
+        if a > cur_e:
+            busy += cur_e - cur_s
+            cur_s, cur_e = a, b_
+        else:
+            cur_e = max(cur_e, b_)
+    busy += cur_e - cur_s
+    print(f"stream {k}: {len(iv) / N:.0f} kernels/step, busy {busy / N:.1f} us/step, summed durations "
+          f"{sum(b_ - a for a, b_ in iv) / N:.1f} us/step")
 tot = sum(v[1] for v in agg.values())
 print(f"steps {N}: span {(tmax - tmin) / N:.1f} us/step, sum of kernel time {tot / N:.1f} us/step, kernels/step {len(ev) / N:.0f}")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"{v[1] / N:9.1f} us/step {v[0] / N:6.1f} x {v[1] / v[0]:7.2f} us  {k[:80]}")
