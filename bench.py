@@ -353,9 +353,10 @@ def run_ours(args):
         kernels_per_step = _lib.kernel_count - k0
         step_flops = eng.flops_per_step(B)
         achieved = probe["tflops"]
-        cpu, _ = cpu_baseline()
+        # CPU legs: rank 0 at N = 1 only (under torchrun every rank is pinned to OMP_NUM_THREADS=1)
+        cpu = cpu_baseline()[0] if world == 1 else None
         fed_roof = fedavg_roofline(eng, dev, peak_hbm)
-        fed_cpu = cpu_fedavg_baseline(eng.n_update)
+        fed_cpu = cpu_fedavg_baseline(eng.n_update) if world == 1 else None
         value = world * B * K / t_dev
         img_bytes = pool[0]["img"].numel() * 4 + pool[0]["label"].numel() * 8
         traffic = roofline_traffic()
