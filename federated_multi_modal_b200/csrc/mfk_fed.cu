@@ -40,48 +40,91 @@ __device__ __forceinline__ float4 load4<__half>(const __half* p, long long i) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ---- fixed-order reduction of one float4 column group over the K client rows.
+// The pointer table and the weights are staged in shared memory once per block (a pointer fetched from global memory
+// in front of every row load serialised two DRAM round trips per client), and the rows are fetched EIGHT AT A TIME
+// — independent 16-byte loads issued back to back — before the (order-preserving) additions: the reduction is a
+// pure streaming pass and needs ~40 KB in flight per SM to reach the HBM rate (ncu, v16: 3.3 TB/s of 6.5, 41 % ALU:
+// dependent loads and four branchy isnan / isinf tests per element). NaN / Inf are detected on the raw exponent
+// bits of the whole group; the per-element nan_to_num path runs only when one is present.
+constexpr int FED_TABLE = 64;   // clients whose pointers / weights are staged in shared memory
+constexpr int FED_BATCH = 8;    // rows in flight per thread
+
+template <typename TIN>
+__device__ __forceinline__ float4 fed_load_row(const TIN* p, long long i, long long n) {
+  if (i + 3 < n && vec_ok(p, i)) return load4<TIN>(p, i);
+  float4 v;
+  v.x = (float)p[i];
+  v.y = i + 1 < n ? (float)p[i + 1] : 0.f;
+  v.z = i + 2 < n ? (float)p[i + 2] : 0.f;
+  v.w = i + 3 < n ? (float)p[i + 3] : 0.f;
+  return v;
+}
+__device__ __forceinline__ bool nonfinite_bits(float v) { return (__float_as_uint(v) & 0x7F800000u) == 0x7F800000u; }
+
+template <typename TIN>
+__device__ __forceinline__ float4 fed_reduce4(const void* const* ptrs, const float* weights, int K, long long i,
+                                              long long n, int* flags) {
+  float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 chunk = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k0 = 0; k0 < K; k0 += FED_BATCH) {
+    float4 v[FED_BATCH];
+#pragma unroll
+    for (int j = 0; j < FED_BATCH; ++j)
+      if (k0 + j < K) v[j] = fed_load_row<TIN>(static_cast<const TIN*>(ptrs[k0 + j]), i, n);
+#pragma unroll
+    for (int j = 0; j < FED_BATCH; ++j) {
+      const int k = k0 + j;
+      if (k < K) {
+        float4 x = v[j];
+        if (nonfinite_bits(x.x) | nonfinite_bits(x.y) | nonfinite_bits(x.z) | nonfinite_bits(x.w)) {
+          bool bn = false, bi = false;
+          x.x = sanitize(x.x, flags, bn, bi); x.y = sanitize(x.y, flags, bn, bi);
+          x.z = sanitize(x.z, flags, bn, bi); x.w = sanitize(x.w, flags, bn, bi);
+          if (flags) atomicOr(&flags[k], (bn ? 1 : 0) | (bi ? 2 : 0));
+        }
+        if (weights) {
+          const float w = weights[k];
+          x.x = __fmul_rn(x.x, w); x.y = __fmul_rn(x.y, w); x.z = __fmul_rn(x.z, w); x.w = __fmul_rn(x.w, w);
+        }
+        // explicit __fadd_rn: no FMA contraction, the order is the contract (sequential inside chunks of 16 clients,
+        // chunk sums added sequentially, remainder last)
+        const int pos = k & 15;
+        if (pos == 0) chunk = x;
+        else { chunk.x = __fadd_rn(chunk.x, x.x); chunk.y = __fadd_rn(chunk.y, x.y); chunk.z = __fadd_rn(chunk.z, x.z); chunk.w = __fadd_rn(chunk.w, x.w); }
+        if (pos == 15 || k == K - 1) {
+          if (k < 16) total = chunk;
+          else { total.x = __fadd_rn(total.x, chunk.x); total.y = __fadd_rn(total.y, chunk.y); total.z = __fadd_rn(total.z, chunk.z); total.w = __fadd_rn(total.w, chunk.w); }
+        }
+      }
+    }
+  }
+  return total;
+}
+
+// stage the first min(K, FED_TABLE) table entries in shared memory; returns the tables to read from
+struct FedTables { const void* const* ptrs; const float* weights; };
+__device__ __forceinline__ FedTables fed_stage_tables(const void* const* ptrs, const float* weights, int K,
+                                                      const void** s_ptrs, float* s_w) {
+  if (K > FED_TABLE) return {ptrs, weights};
+  if ((int)threadIdx.x < K) {
+    s_ptrs[threadIdx.x] = ptrs[threadIdx.x];
+    if (weights) s_w[threadIdx.x] = weights[threadIdx.x];
+  }
+  __syncthreads();
+  return {s_ptrs, weights ? s_w : nullptr};
+}
+
 template <typename TIN>
 __global__ void __launch_bounds__(256)
 fedavg_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ weights, int K, long long n,
               float divisor, float* __restrict__ out32, __half* __restrict__ out16, int* __restrict__ flags) {
+  __shared__ const void* s_ptrs[FED_TABLE];
+  __shared__ float s_w[FED_TABLE];
+  const FedTables tb = fed_stage_tables(ptrs, weights, K, s_ptrs, s_w);
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-    float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 chunk = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int full = K / 16;
-    for (int k = 0; k < K; ++k) {
-      const TIN* p = static_cast<const TIN*>(ptrs[k]);
-      float4 v;
-      if (i + 3 < n && vec_ok(p, i)) {
-        v = load4<TIN>(p, i);
-      } else if (i + 3 < n) {
-        v = make_float4((float)p[i], (float)p[i + 1], (float)p[i + 2], (float)p[i + 3]);
-      } else {
-        v.x = (float)p[i];
-        v.y = i + 1 < n ? (float)p[i + 1] : 0.f;
-        v.z = i + 2 < n ? (float)p[i + 2] : 0.f;
-        v.w = 0.f;
-      }
-      bool bn = false, bi = false;
-      v.x = sanitize(v.x, flags, bn, bi); v.y = sanitize(v.y, flags, bn, bi);
-      v.z = sanitize(v.z, flags, bn, bi); v.w = sanitize(v.w, flags, bn, bi);
-      if (flags && (bn || bi)) atomicOr(&flags[k], (bn ? 1 : 0) | (bi ? 2 : 0));
-      if (weights) {
-        const float w = weights[k];
-        v.x = __fmul_rn(v.x, w); v.y = __fmul_rn(v.y, w); v.z = __fmul_rn(v.z, w); v.w = __fmul_rn(v.w, w);
-      }
-      // explicit __fadd_rn: no FMA contraction, order is the contract
-      const int pos = k & 15;
-      if (pos == 0) chunk = v;
-      else { chunk.x = __fadd_rn(chunk.x, v.x); chunk.y = __fadd_rn(chunk.y, v.y); chunk.z = __fadd_rn(chunk.z, v.z); chunk.w = __fadd_rn(chunk.w, v.w); }
-      const bool chunk_done = (pos == 15) || (k == K - 1);
-      if (chunk_done) {
-        const int ci = k / 16;
-        if (ci == 0) total = chunk;
-        else { total.x = __fadd_rn(total.x, chunk.x); total.y = __fadd_rn(total.y, chunk.y); total.z = __fadd_rn(total.z, chunk.z); total.w = __fadd_rn(total.w, chunk.w); }
-      }
-    }
-    (void)full;
+    const float4 total = fed_reduce4<TIN>(tb.ptrs, tb.weights, K, i, n, flags);
     float4 m;
     m.x = __fdiv_rn(total.x, divisor); m.y = __fdiv_rn(total.y, divisor);
     m.z = __fdiv_rn(total.z, divisor); m.w = __fdiv_rn(total.w, divisor);
@@ -109,38 +152,12 @@ __global__ void __launch_bounds__(256)
 fedavg_scatter_kernel(const void* const* __restrict__ ptrs, const float* __restrict__ weights, int K, long long n,
                       long long lo, long long hi, float divisor, float* const* __restrict__ out32,
                       __half* const* __restrict__ out16, int W) {
+  __shared__ const void* s_ptrs[FED_TABLE];
+  __shared__ float s_w[FED_TABLE];
+  const FedTables tb = fed_stage_tables(ptrs, weights, K, s_ptrs, s_w);
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
-    float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 chunk = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < K; ++k) {
-      const float* p = static_cast<const float*>(ptrs[k]);
-      float4 v;
-      if (i + 3 < n && vec_ok(p, i)) {
-        v = load4<float>(p, i);
-      } else if (i + 3 < n) {
-        v = make_float4(p[i], p[i + 1], p[i + 2], p[i + 3]);
-      } else {
-        v.x = p[i];
-        v.y = i + 1 < n ? p[i + 1] : 0.f;
-        v.z = i + 2 < n ? p[i + 2] : 0.f;
-        v.w = 0.f;
-      }
-      bool bn = false, bi = false;
-      v.x = sanitize(v.x, nullptr, bn, bi); v.y = sanitize(v.y, nullptr, bn, bi);
-      v.z = sanitize(v.z, nullptr, bn, bi); v.w = sanitize(v.w, nullptr, bn, bi);
-      if (weights) {
-        const float w = weights[k];
-        v.x = __fmul_rn(v.x, w); v.y = __fmul_rn(v.y, w); v.z = __fmul_rn(v.z, w); v.w = __fmul_rn(v.w, w);
-      }
-      const int pos = k & 15;
-      if (pos == 0) chunk = v;
-      else { chunk.x = __fadd_rn(chunk.x, v.x); chunk.y = __fadd_rn(chunk.y, v.y); chunk.z = __fadd_rn(chunk.z, v.z); chunk.w = __fadd_rn(chunk.w, v.w); }
-      if (pos == 15 || k == K - 1) {
-        if (k / 16 == 0) total = chunk;
-        else { total.x = __fadd_rn(total.x, chunk.x); total.y = __fadd_rn(total.y, chunk.y); total.z = __fadd_rn(total.z, chunk.z); total.w = __fadd_rn(total.w, chunk.w); }
-      }
-    }
+    const float4 total = fed_reduce4<float>(tb.ptrs, tb.weights, K, i, n, nullptr);
     float4 m;
     m.x = __fdiv_rn(total.x, divisor); m.y = __fdiv_rn(total.y, divisor);
     m.z = __fdiv_rn(total.z, divisor); m.w = __fdiv_rn(total.w, divisor);
