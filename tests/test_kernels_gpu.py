@@ -508,3 +508,49 @@ def test_gpu_augmentation_matches_torchvision():
         n_off += int((lsb > 0.5).sum())
     assert worst <= 1.01, worst
     assert n_off <= 2e-3 * B * 3 * S * S, n_off
+
+
+def test_fedavg_unaligned_rows_and_guarded_sgd():
+    """(a) client rows whose addresses are NOT 16-byte aligned (rows of a packed [K, n] buffer with
+    n % 4 != 0, fp16 views at odd offsets) must reduce bit-exactly through the element-load path instead of faulting;
+    (b) the fused clip+SGD step leaves parameters and momentum untouched when the loss or the input flag is bad, and
+    a NaN gradient norm propagates (torch.clamp semantics), it is not replaced by 'no clipping'."""
+    from oracle.maple_cpu import fedavg_oracle
+    K, n = 5, 1001
+    g = torch.Generator().manual_seed(3)
+    packed = torch.randn(K * n + 3, generator=g)
+    base = packed.to(DEV)
+    rows = [base[1 + k * n: 1 + (k + 1) * n] for k in range(K)]        # 4-byte aligned only
+    assert any(r.data_ptr() % 16 for r in rows)
+    ptrs = torch.tensor([r.data_ptr() for r in rows], dtype=torch.int64, device=DEV)
+    out = torch.empty(n + 1, device=DEV)[1:]                            # misaligned output too
+    ops.fedavg_reduce(ptrs, None, float(K), K, n, False, out, None, None)
+    want = fedavg_oracle([packed[1 + k * n: 1 + (k + 1) * n] for k in range(K)])[0]
+    assert torch.equal(out.cpu(), want)
+    h = packed.half().to(DEV)
+    hrows = [h[1 + k * n: 1 + (k + 1) * n] for k in range(K)]
+    ptrs = torch.tensor([r.data_ptr() for r in hrows], dtype=torch.int64, device=DEV)
+    out16 = torch.empty(n + 1, device=DEV, dtype=torch.float16)[1:]
+    ops.fedavg_reduce(ptrs, None, float(K), K, n, True, None, out16, None)
+    assert torch.equal(out16.cpu(), fedavg_oracle([packed.half()[1 + k * n: 1 + (k + 1) * n] for k in range(K)])[1])
+    # ---- guarded update
+    m = 4096
+    p0, g0 = rnd(m, seed=60), rnd(m, std=0.1, seed=61)
+    hp = torch.tensor([0.01, 0.9, 0.0, 5e-4, 1.0, 0.0, 1.0], device=DEV)
+    ws, norm = torch.empty(296, device=DEV), torch.empty(1, device=DEV)
+    for loss_v, flag_v in ((float("nan"), 0), (float("inf"), 0), (1.0, 1), (1.0, 2)):
+        p, gg, mom = p0.clone(), g0.clone(), torch.zeros(m, device=DEV)
+        ops.grad_norm(gg, ws, norm)
+        ops.sgd_step(p, gg, mom, hp, norm, m, torch.tensor([loss_v], device=DEV),
+                     torch.tensor([flag_v], device=DEV, dtype=torch.int32))
+        assert torch.equal(p, p0) and float(mom.abs().max()) == 0.0 and torch.equal(gg, g0), (loss_v, flag_v)
+    p, gg, mom = p0.clone(), g0.clone(), torch.zeros(m, device=DEV)
+    ops.grad_norm(gg, ws, norm)
+    ops.sgd_step(p, gg, mom, hp, norm, m, torch.tensor([1.0], device=DEV), torch.zeros(1, device=DEV, dtype=torch.int32))
+    assert not torch.equal(p, p0)
+    p, gg, mom = p0.clone(), g0.clone(), torch.zeros(m, device=DEV)
+    gg[7] = float("nan")
+    ops.grad_norm(gg, ws, norm)
+    assert torch.isnan(norm).item()
+    ops.sgd_step(p, gg, mom, hp, norm, m, torch.tensor([1.0], device=DEV), torch.zeros(1, device=DEV, dtype=torch.int32))
+    assert torch.isnan(p).all().item()     # clip coefficient NaN * every gradient, as torch.clamp(max_norm / (norm + eps)) does

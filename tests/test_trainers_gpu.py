@@ -212,3 +212,46 @@ def test_pipelined_epoch_and_eval_match_plain_loops():
         outs.append((t.model.engine.params.clone(), acc))
     assert torch.equal(outs[0][0], outs[1][0])
     assert outs[0][1] == outs[1][1]
+
+
+def test_load_state_dict_reaches_frozen_tensors_and_failed_step_keeps_weights():
+    """(medium) CustomCLIP.load_state_dict must push EVERY tensor to the kernels (frozen block weights,
+    logit_scale, embeddings, prompt prefix / suffix), not only those with requires_grad; (low) a step rejected for
+    a NaN image must leave the model exactly as it was (the reference raises before optim.step())."""
+    img, lab = synth.make_batch(4, 10, 123)
+    t = _trainer(False)
+    t.model.eval()
+    before = t.model(img.cuda()).clone()
+    sd = {k: v.clone() for k, v in torch.nn.Module.state_dict(t.model).items()}
+    sd["logit_scale"] = sd["logit_scale"] + 0.25
+    k_frozen = "image_encoder.transformer.resblocks.3.mlp.c_fc.weight"
+    sd[k_frozen] = (sd[k_frozen].float() * 1.05).to(sd[k_frozen].dtype)
+    sd["clip_model2.visual.transformer.resblocks.3.mlp.c_fc.weight"] = sd[k_frozen]
+    sd["text_encoder.positional_embedding"] = sd["text_encoder.positional_embedding"] * 0.5
+    sd["clip_model2.positional_embedding"] = sd["text_encoder.positional_embedding"]
+    sd["prompt_learner.token_suffix"] = sd["prompt_learner.token_suffix"].flip(0)
+    t.model.load_state_dict(sd, strict=True)
+    after = t.model(img.cuda()).clone()
+    assert not torch.equal(before, after)
+    # a fresh model built around the same tensors gives the same logits
+    t2 = _trainer(False)
+    t2.model.load_state_dict(sd, strict=True)
+    t2.model.eval()
+    assert torch.equal(t2.model(img.cuda()), after)
+    fresh = t2.model.engine.logits(img.cuda(), cache_text=False)
+    assert torch.equal(fresh, after)
+    # ---- rejected step: parameters, momentum and the bf16 copies stay as they were
+    t.model.train()
+    t.forward_backward({"img": img, "label": lab})                  # one good step (momentum now non-zero)
+    eng = t.model.engine
+    snap = (eng.params.clone(), eng.momentum.clone(), eng.vis.w[11]["mlp.c_fc.w"].clone())
+    bad = img.clone(); bad[1, 2, 3, 4] = float("nan")
+    for graph in (False, True):
+        t._use_graph = graph
+        with pytest.raises(ValueError, match="NaN"):
+            t.forward_backward({"img": bad, "label": lab})
+        torch.cuda.synchronize()
+        assert torch.equal(eng.params, snap[0]) and torch.equal(eng.momentum, snap[1])
+        assert torch.equal(eng.vis.w[11]["mlp.c_fc.w"], snap[2])
+    out = t.forward_backward({"img": img, "label": lab})            # training continues normally afterwards
+    assert out["loss"] > 0 and not torch.equal(eng.params, snap[0])
