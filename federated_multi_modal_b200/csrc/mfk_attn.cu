@@ -477,10 +477,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* s_full = bars + 3;      // [2] per query tile / group
   uint64_t* o_full = bars + 5;      // [2]
   uint64_t* tmem_free = bars + 7;   // [2]
-  uint64_t* p_full = bars + 9;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  float* sx = reinterpret_cast<float*>(smem_raw_tc + 128);  // [2 groups][2 halves][128 rows] max / sum exchange
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 128 + 2048 + 1023) &
+  uint64_t* p_full = bars + 9;      // [2][4] per group and 64-key block of P: P V starts on block 0 while the
+                                    //        softmax warps are still exponentiating the later blocks
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* sx = reinterpret_cast<float*>(smem_raw_tc + 256);  // [2 groups][2 halves][128 rows] max / sum exchange
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 256 + 2048 + 1023) &
                                              ~uintptr_t(1023));
   const int Tk = p.Tk, D = p.heads * HD, NT = p.m_tiles;
   const uint32_t kvBytes = (uint32_t)Tk * 128u, qBytes = (uint32_t)NT * 16384u;
@@ -506,7 +507,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(&s_full[b], 1);
         mbar_init(&o_full[b], 1);
         mbar_init(&tmem_free[b], TC_SOFTMAX_WARPS);
-        mbar_init(&p_full[b], TC_SOFTMAX_WARPS);
+        for (int k = 0; k < 4; ++k) mbar_init(&p_full[b * 4 + k], TC_SOFTMAX_WARPS);
       }
       fence_barrier_init();
     }
@@ -576,12 +577,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full[mt]);
         mbar_wait(v_full, par);
-        mbar_wait(&p_full[mt], par);
-        tc_fence_after();
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t pa = umma_desc_k_sw128(pbase + (uint32_t)(ks >> 2) * 16384u) + 2ull * (ks & 3);
-          const uint64_t vb = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
-          umma_bf16(d_tmem, pa, vb, idesc_o, ks > 0 ? 1u : 0u);
+        // O accumulates into columns [0, 64) of the S buffer: block 0 of S has been read by every softmax warp once
+        // p_full[0] completes, and no later block touches those columns, so the P V MMAs of block k are issued as soon
+        // as block k of P is staged (they run under the exp pass of the later blocks instead of after it).
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&p_full[mt * 4 + kb], par);
+          tc_fence_after();
+          const int ks_end = min(ksteps, kb * 4 + 4);
+          for (int ks = kb * 4; ks < ks_end; ++ks) {
+            const uint64_t pa = umma_desc_k_sw128(pbase + (uint32_t)kb * 16384u) + 2ull * (ks & 3);
+            const uint64_t vb = umma_desc_mn_sw128(vbase + (uint32_t)ks * 2048u, 1024);
+            umma_bf16(d_tmem, pa, vb, idesc_o, ks > 0 ? 1u : 0u);
+          }
         }
         umma_commit(&o_full[mt]);
       }
@@ -594,14 +601,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int rl = q * 32 + lane;  // row inside the 128-row tile == TMEM lane
     const uint32_t x7 = (uint32_t)rl & 7u;
     float* gsx = sx + mt * 256;
-    const int pair_bar = 1 + mt * 4 + q, grp_bar = 9 + mt;
+    const int pair_bar = 1 + mt * 4 + q;
     auto pair_sync_g = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
-    auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(grp_bar) : "memory"); };
     const uint32_t pbuf = smem_u32(sP) + (uint32_t)mt * pBytes;
     const uint32_t prow = pbuf + (uint32_t)rl * 128u;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mt * 256u;
     const int row = mt * 128 + rl;  // query index inside the sequence
     const int kmax = CAUSAL ? min(p.T, row + 1) : p.T;  // keys [0, kmax) are visible
+    // a warp whose 32 query rows all lie beyond T (T = 199: the last quarter of the second tile) only keeps the
+    // barrier protocol going: no TMEM loads, no exponentials, no stores
+    const bool live = mt * 128 + q * 32 < p.T;
     int ftrc_n = 0;
     for (int u = 0; u < n_units; ++u) {
       int n, h;
@@ -612,20 +621,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       FTRC();  // S ready
       float mx = -INFINITY;
-      for (int c = half * 32; c < Tk; c += 64) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
-        tc_wait_ld();
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: ILP instead of a 32-deep dependency
-        if (!CAUSAL && c + 32 <= p.T) {
+      if (live) {
+        for (int c = half * 32; c < Tk; c += 64) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c, r);
+          tc_wait_ld();
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: ILP instead of a 32-deep dependency
+          if (!CAUSAL && c + 32 <= p.T) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[j]));
-        } else {
+            for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[j]));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            m4[j & 3] = fmaxf(m4[j & 3], (c + j < kmax) ? __uint_as_float(r[j]) : -INFINITY);
+            for (int j = 0; j < 32; ++j)
+              m4[j & 3] = fmaxf(m4[j & 3], (c + j < kmax) ? __uint_as_float(r[j]) : -INFINITY);
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
       gsx[half * 128 + rl] = mx;
       pair_sync_g();
@@ -633,53 +644,59 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mx = fmaxf(mx, gsx[(half ^ 1) * 128 + rl]);
       const float mc = (mx == -INFINITY) ? 0.f : mx * p.c1;
       float l = 0.f;
-      for (int c = half * 32; c < Tk; c += 64) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
-        tc_wait_ld();
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[16];
-        if (!CAUSAL && c + 32 <= p.T) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int c = kb * 64 + half * 32;
+        if (live && c < Tk) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c, r);
+          tc_wait_ld();
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t pk[16];
+          if (!CAUSAL && c + 32 <= p.T) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = fast_exp2(__uint_as_float(r[2 * j]) * p.c1 - mc);
-            const float e1 = fast_exp2(__uint_as_float(r[2 * j + 1]) * p.c1 - mc);
-            l4[j & 3] += e0 + e1;
-            pk[j] = pack_bf16(e0, e1);
-          }
-        } else {
+            for (int j = 0; j < 16; ++j) {
+              const float e0 = fast_exp2(__uint_as_float(r[2 * j]) * p.c1 - mc);
+              const float e1 = fast_exp2(__uint_as_float(r[2 * j + 1]) * p.c1 - mc);
+              l4[j & 3] += e0 + e1;
+              pk[j] = pack_bf16(e0, e1);
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = (c + 2 * j < kmax) ? fast_exp2(__uint_as_float(r[2 * j]) * p.c1 - mc) : 0.f;
-            const float e1 = (c + 2 * j + 1 < kmax) ? fast_exp2(__uint_as_float(r[2 * j + 1]) * p.c1 - mc) : 0.f;
-            l4[j & 3] += e0 + e1;
-            pk[j] = pack_bf16(e0, e1);
+            for (int j = 0; j < 16; ++j) {
+              const float e0 = (c + 2 * j < kmax) ? fast_exp2(__uint_as_float(r[2 * j]) * p.c1 - mc) : 0.f;
+              const float e1 = (c + 2 * j + 1 < kmax) ? fast_exp2(__uint_as_float(r[2 * j + 1]) * p.c1 - mc) : 0.f;
+              l4[j & 3] += e0 + e1;
+              pk[j] = pack_bf16(e0, e1);
+            }
           }
+          l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+          const uint32_t blk = prow + (uint32_t)kb * 16384u;
+          const uint32_t ch0 = (uint32_t)half * 4u;  // first 16-byte chunk of this 32-column group: 0 or 4
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((ch0 + j) ^ x7) << 4)), "r"(pk[4 * j]),
+                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
         }
-        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        const uint32_t blk = prow + (uint32_t)(c >> 6) * 16384u;
-        const uint32_t ch0 = (uint32_t)(c & 63) >> 3;  // first 16-byte chunk of this 32-column group: 0 or 4
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((ch0 + j) ^ x7) << 4)), "r"(pk[4 * j]),
-                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                       : "memory");
+        // block kb of P is staged by this warp (or is not its business): its P V MMAs may go
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[mt * 4 + kb]);
       }
       pair_sync_g();                       // both warps have read the partner's max: the slot can be reused
       gsx[half * 128 + rl] = l;
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[mt]);
       FTRC();  // pass 2 (exp, P staged) done
       pair_sync_g();
       l += gsx[(half ^ 1) * 128 + rl];
-      // ---- epilogue: O = (P V) / l -> bf16 staged in this group's (now idle) P buffer -> coalesced row stores
+      // ---- epilogue: O = (P V) / l -> bf16, staged by THIS warp in its own 32 rows x 64 bytes of the group's (now
+      // idle) P buffer and copied out by the same warp as 64-byte row segments (8 rows per instruction): no
+      // group-wide barrier, the other warps of the group are already on their way to the next unit
       mbar_wait(&o_full[mt], par);
       tc_fence_after();
       FTRC();  // O = P V ready
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      {
+      if (live) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)(half * 32), r);
         tc_wait_ld();
@@ -691,26 +708,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                        "r"(pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv)),
                        "r"(pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv))
                        : "memory");
+        if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
       }
-      if (p.lse && half == 0 && row < p.T) p.lse[((size_t)n * p.heads + h) * p.T + row] = mc + log2f(l);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_free[mt]);
-      group_sync();
-      const int tid = (int)threadIdx.x & 255;
+      if (live) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int idx = tid + m * 256;
-        const int r_ = idx >> 3, ch = idx & 7;
-        if (mt * 128 + r_ < p.T) {
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(pbuf + (uint32_t)r_ * 128u + (((uint32_t)ch ^ ((uint32_t)r_ & 7u)) << 4)));
-          *reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T + mt * 128 + r_) * D + h * HD + ch * 8) = v;
+        for (int m = 0; m < 4; ++m) {
+          const int idx = lane + m * 32;
+          const int r_ = q * 32 + (idx >> 2), ch = half * 4 + (idx & 3);
+          if (mt * 128 + r_ < p.T) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(pbuf + (uint32_t)r_ * 128u + (((uint32_t)ch ^ ((uint32_t)r_ & 7u)) << 4)));
+            *reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T + mt * 128 + r_) * D + h * HD + ch * 8) = v;
+          }
         }
+        __syncwarp();  // the staged rows are overwritten by this warp's next P chunk: every lane has read its part
       }
-      group_sync();  // the buffer is overwritten by the next unit's P: every thread must have read its part
       FTRC();  // epilogue done
     }
   }
