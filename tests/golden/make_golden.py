@@ -18,6 +18,7 @@ Outputs (small, committed): tests/golden/*.pt
                prompt-learner tensor + strided samples of the other trainable tensors. Also the loss
                sequence of the reference AS-IS (PREC=fp16: SGD applied to fp16 parameters in place) to
                quantify the fp32-master vs fp16-in-place difference.
+  edge_n4d12_fp32.pt / edge_n2d1_fp32.pt  other prompt configurations (N_CTX=4, PROMPT_DEPTH=12; PROMPT_DEPTH=1), B=2, C=3.
   ckpt_spec.pt the checkpoint dict MaPLeFederated.save_model hands to Dassl's save_checkpoint
                (trainers/maple_fed.py:367-386): target directory, top-level keys, and key/shape/dtype of
                the state_dict before and after one safe_average_weights aggregation.
@@ -48,16 +49,16 @@ def pack_grad(g: torch.Tensor):
                 sum=flat.double().sum().item(), shape=tuple(g.shape))
 
 
-def run_case(B, C, seed_clip=0, seed_pl=1, seed_batch=123, fp32=True):
+def run_case(B, C, seed_clip=0, seed_pl=1, seed_batch=123, fp32=True, n_ctx=2, depth=9):
     torch.manual_seed(0)
-    cfg = synth.make_cfg()
+    cfg = synth.make_cfg(n_ctx=n_ctx, depth=depth)
     names = synth.synthetic_classnames(C)
     sd = synth.random_clip_state_dict(seed_clip)
-    pl = synth.random_prompt_learner_state(seed_pl)
+    pl = synth.random_prompt_learner_state(seed_pl, n_ctx=n_ctx, depth=depth)
     model = rh.build_reference_customclip(sd, names, cfg, pl, fp32=fp32)
     img, lab = synth.make_batch(B, C, seed_batch)
     out = dict(meta=dict(B=B, C=C, seed_clip=seed_clip, seed_pl=seed_pl, seed_batch=seed_batch,
-                         n_ctx=2, depth=9, fp32=fp32, torch=torch.__version__))
+                         n_ctx=n_ctx, depth=depth, fp32=fp32, torch=torch.__version__))
     model.eval()
     feats = {}
     with torch.no_grad():
@@ -76,7 +77,7 @@ def run_case(B, C, seed_clip=0, seed_pl=1, seed_batch=123, fp32=True):
     for tower, blocks in (("vis", model.image_encoder.transformer.resblocks),
                           ("txt", model.text_encoder.transformer.resblocks)):
         for li in (0, 1, 8, 11):
-            def mk(name):
+            def mk(name):  # noqa: E306
                 def hook(mod, inp, outp):
                     x = outp[0].detach().permute(1, 0, 2)  # LND -> NLD
                     acts[name] = x[:2, ::16, ::8].clone()  # small strided sample
@@ -188,6 +189,24 @@ def checkpoint_spec():
                 ctx_after=st["state_dict"]["prompt_learner.ctx"].clone())
 
 
+def edge_cases():
+    """Other prompt configurations of the reference (cfg.TRAINER.MAPLE.N_CTX / PROMPT_DEPTH): the deepest and widest
+    the CTX_INIT path allows (n_ctx=4, depth=12: prompts spliced into layers 1..11, T_v = 201) and the shallowest
+    (depth=1: no deep prompts, no compound projections). B=2, C=3."""
+    torch.set_num_threads(8)
+    for tag, n_ctx, depth in (("n4d12", 4, 12), ("n2d1", 2, 1)):
+        o, _ = run_case(2, 3, seed_batch=77, n_ctx=n_ctx, depth=depth)
+        torch.save(o, os.path.join(HERE, f"edge_{tag}_fp32.pt"))
+        print(tag, "loss", o["loss"].item(), "grads", o["n_with_grad"], "/", o["n_trainable"])
+
+
+if __name__ == "__main__" and "--edge-only" in sys.argv:
+    import contextlib, io
+    with contextlib.redirect_stderr(io.StringIO()):
+        edge_cases()
+    sys.exit(0)
+
+
 def extra_cases():
     torch.set_num_threads(8)
     o2, _ = run_case(32, 10, seed_batch=2032)
@@ -218,6 +237,7 @@ if __name__ == "__main__":
     import contextlib, io
     torch.set_num_threads(8)
     extra_cases()
+    edge_cases()
     o, _ = run_case(4, 10)
     torch.save(o, os.path.join(HERE, "c1_fp32.pt"))
     print("c1 loss", o["loss"].item(), "grads", o["n_with_grad"], "/", o["n_trainable"])

@@ -253,3 +253,40 @@ def test_eval_graph_replay_equals_eager_across_updates_and_clients(c1):
     ref2.eval_graph = False
     ref2.params.copy_(eng.params); ref2.repack_trainable(); ref2._text_cache_valid = False
     assert torch.equal(c_eng, ref2.logits(img))
+
+
+@pytest.mark.parametrize("fixture", ["edge_n4d12_fp32.pt", "edge_n2d1_fp32.pt"])
+def test_other_prompt_configurations_vs_reference_golden(fixture):
+    """cfg.TRAINER.MAPLE.N_CTX / PROMPT_DEPTH other than the yaml's 2 / 9: N_CTX=4 with prompts spliced into layers
+    1..11 (T_v = 201, 11 compound projections) and PROMPT_DEPTH=1 (no deep prompts at all). Fixtures are the
+    unmodified reference's outputs (tests/golden/make_golden.py::edge_cases)."""
+    G = load_golden(fixture)
+    m = G["meta"]
+    sd, tok = customclip_state_dict(m["C"], m["seed_clip"], m["seed_pl"], n_ctx=m["n_ctx"], depth=m["depth"])
+    img, lab = synth.make_batch(m["B"], m["C"], m["seed_batch"])
+    eng = MapleEngine(sd, tok, n_ctx=m["n_ctx"], depth=m["depth"])
+    assert eng.Tv == 197 + m["n_ctx"]
+    lg = eng.logits(img.cuda()).cpu()
+    assert _rel(lg, G["logits_eval"]) < 1e-2
+    assert _rel(eng.logits(img.cuda(), precision="fp32").cpu(), G["logits_eval"]) < 1e-3
+    loss, logits = eng.forward_backward(img.cuda(), lab.cuda())
+    assert abs(loss.item() - G["loss"].item()) < 2e-2 * G["loss"].item()
+    # training-mode logits are internal (they only feed the loss; CustomCLIP.forward returns logits in eval mode only)
+    # and come from the all-bf16 text tower: with 3 classes the logits are tiny (max |logit| 0.31 at PROMPT_DEPTH=1),
+    # so their error (7e-3 absolute, the same as at every other shape) is bounded on the absolute scale here
+    assert (logits.cpu() - G["logits_eval"]).abs().max().item() < 2e-2 * max(1.0, G["logits_eval"].abs().max().item())
+    assert set(G["grads"]) <= set(eng.g) and len(G["grads"]) == 145 + 3 * (m["depth"] - 9)
+    cos, rel = {}, {}
+    for name, packed in G["grads"].items():
+        g = eng.g[name].cpu()
+        ref = packed["full"] if "full" in packed else packed["sample"]
+        got = g if "full" in packed else g.reshape(-1)[::packed["stride"]]
+        cos[name] = torch.nn.functional.cosine_similarity(got.reshape(-1).double(), ref.reshape(-1).double(), dim=0).item()
+        rel[name] = _rel(got, ref)
+    low = sorted(cos.items(), key=lambda kv: kv[1])[:4]
+    print(fixture, "lowest grad cosine vs reference autograd:", low, "largest max-rel:", sorted(rel.items(), key=lambda kv: -kv[1])[:3])
+    assert low[0][1] > 0.99, low
+    assert max(rel.values()) < 0.1
+    # one fused optimiser step runs on this layout too
+    eng.sgd_step(lr=0.0026)
+    assert torch.isfinite(eng.params).all()
