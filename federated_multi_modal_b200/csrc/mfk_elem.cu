@@ -7,6 +7,10 @@ namespace {
 using namespace mfk;
 
 constexpr int kLnWarps = 8;
+#ifndef MFK_LNF_WARPS
+#define MFK_LNF_WARPS 8
+#endif
+constexpr int kLnFwdWarps = MFK_LNF_WARPS;  // rows (= warps) per CTA of the forward kernel
 
 // ============================================================================ LayerNorm forward
 // clip/model.py:153-159: fp32 LayerNorm (eps 1e-5, biased variance). One warp per row,
@@ -46,7 +50,7 @@ __device__ __forceinline__ void ln_row_write(const float4 (&v)[VEC], float mean,
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnFwdWarps * 32)
 ln_fwd_kernel(float* __restrict__ x, const int* __restrict__ rowidx, const float* __restrict__ gamma,
               const float* __restrict__ beta, bf16* __restrict__ y16, float* __restrict__ y32,
               float* __restrict__ xsave, float* __restrict__ mean_o, float* __restrict__ rstd_o, int M, float eps,
@@ -55,7 +59,7 @@ ln_fwd_kernel(float* __restrict__ x, const int* __restrict__ rowidx, const float
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int row = blockIdx.x * kLnFwdWarps + (threadIdx.x >> 5);
   if (row >= M) return;
   const size_t src = rowidx ? (size_t)rowidx[row] : (size_t)row;
   float4* xr = reinterpret_cast<float4*>(x + src * D);
@@ -759,11 +763,11 @@ extern "C" int mfk_layernorm_fwd_splice(float* x, const int* rowidx, const float
   if (!x || !gamma || !beta || M <= 0) return MFK_EARG;
   if (!y_bf16 && !y_f32) return MFK_EARG;
   if (prompt && (rowidx || T <= 0 || row0 < 0 || n_ctx <= 0 || row0 + n_ctx > T)) return MFK_EARG;
-  const int grid = (M + kLnWarps - 1) / kLnWarps;
+  const int grid = (M + kLnFwdWarps - 1) / kLnFwdWarps;
   bf16* y16 = static_cast<bf16*>(y_bf16);
-  if (D == 768) launch_pdl(ln_fwd_kernel<6>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
-  else if (D == 512) launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
-  else if (D == 128) launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
+  if (D == 768) launch_pdl(ln_fwd_kernel<6>, dim3(grid), dim3(kLnFwdWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
+  else if (D == 512) launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(kLnFwdWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
+  else if (D == 128) launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(kLnFwdWarps * 32), 0, ST(stream), x, rowidx, gamma, beta, y16, y_f32, x_save, mean, rstd, M, eps, prompt, T, row0, n_ctx);
   else return MFK_ESHAPE;
   MFK_CHECK_LAUNCH();
   return MFK_OK;
