@@ -210,13 +210,24 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, f
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   const long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // four independent 16-byte loads in flight per thread (a pure streaming pass; one load per iteration ran at 48 %
+  // of the HBM rate); the accumulation order per thread is fixed, so the result does not depend on timing
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 a = g4[i], b = g4[i + stride], c = g4[i + 2 * stride], d = g4[i + 3 * stride];
+    s0 += a.x * a.x; s1 += a.y * a.y; s2 += a.z * a.z; s3 += a.w * a.w;
+    s0 += b.x * b.x; s1 += b.y * b.y; s2 += b.z * b.z; s3 += b.w * b.w;
+    s0 += c.x * c.x; s1 += c.y * c.y; s2 += c.z * c.z; s3 += c.w * c.w;
+    s0 += d.x * d.x; s1 += d.y * d.y; s2 += d.z * d.z; s3 += d.w * d.w;
+  }
+  for (; i < n4; i += stride) {
     const float4 v = g4[i];
     s0 += v.x * v.x; s1 += v.y * v.y; s2 += v.z * v.z; s3 += v.w * v.w;
   }
   float s = (s0 + s1) + (s2 + s3);
   if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (long long i = n4 << 2; i < n; ++i) s += g[i] * g[i];
+    for (long long k = n4 << 2; k < n; ++k) s += g[k] * g[k];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -226,12 +237,14 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, f
     partial[blockIdx.x] = t;
   }
 }
+// one warp: lane l adds partials l, l + 32, ... (loads in parallel instead of P dependent ones), then a fixed butterfly
 __global__ void sumsq_final_kernel(const float* __restrict__ partial, int P, float* __restrict__ norm_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float t = 0.f;
-    for (int p = 0; p < P; ++p) t += partial[p];
-    norm_out[0] = sqrtf(t);
-  }
+  pdl_trigger();
+  pdl_wait();
+  float t = 0.f;
+  for (int p = threadIdx.x; p < P; p += 32) t += partial[p];
+  t = warp_sum(t);
+  if (threadIdx.x == 0) norm_out[0] = sqrtf(t);
 }
 // torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.SGD.step (trainers/maple.py:592-598).
 // hp = {lr, momentum, dampening, weight_decay, max_norm, nesterov, first_step}
@@ -331,7 +344,7 @@ extern "C" int mfk_grad_norm(const float* g, long long n, float* partial_ws, flo
   if (!mfk_aligned16(g)) return MFK_EALIGN;
   const int P = 296;
   sumsq_partial_kernel<<<P, 256, 0, ST(stream)>>>(g, n, partial_ws);
-  sumsq_final_kernel<<<1, 32, 0, ST(stream)>>>(partial_ws, P, norm_out);
+  launch_pdl(sumsq_final_kernel, dim3(1), dim3(32), 0, ST(stream), static_cast<const float*>(partial_ws), P, norm_out);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }
