@@ -469,7 +469,7 @@ class MapleEngine:
                           dbeta=G[pre + "ln_1.bias"] if ln_grads else None, splice_grad=splice_grad)
 
     # ------------------------------------------------------------------ towers: embed + head rows
-    def _vision_embed(self, img: torch.Tensor, train: bool):
+    def _vision_embed(self, img: torch.Tensor, train: bool, wait_before_assemble=None):
         B = img.shape[0]
         tw = self.vis
         self._tower_bufs(tw, B, self.Tv, train)
@@ -480,6 +480,8 @@ class MapleEngine:
         p = self.p
         x0 = self._buf("vis.x0", (tw.M, tw.D), F32) if train else None
         self.vstat0 = self._buf("vis.stat0", (2, tw.M), F32)
+        if wait_before_assemble is not None:
+            torch.cuda.current_stream().wait_event(wait_before_assemble)
         ops.vis_assemble_lnpre(tok, self.cls, self.vpos, self.shared, p["image_encoder.ln_pre.weight"],
                                p["image_encoder.ln_pre.bias"], x0, tw.ws["x1"][0], self.vstat0[0], self.vstat0[1], B,
                                self.Tv, self.n)
@@ -514,9 +516,9 @@ class MapleEngine:
         return self._features(tw, xout, rows, p["text_encoder.ln_final.weight"],
                               p["text_encoder.ln_final.bias"], self.tproj_T, "txt", Cn, train)
 
-    def _image_features(self, img, train: bool):
+    def _image_features(self, img, train: bool, wait_before_assemble=None):
         tw, p = self.vis, self.p
-        self._vision_embed(img, train)
+        self._vision_embed(img, train, wait_before_assemble)
         B = img.shape[0]
         key = f"cls_rows{B}"
         if key not in self._bufs:
@@ -754,11 +756,15 @@ class MapleEngine:
         # parallel branches.
         main = torch.cuda.current_stream()
         side = self._side_stream()
-        self._prompt_learner_fwd()
+        # the prompt learner's grouped projections head the side branch: the patch-embedding GEMM of the vision tower
+        # does not depend on them, only the assembly of the token sequence (shared_ctx) does
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            self._prompt_learner_fwd()
+            self._pl_event = torch.cuda.Event()
+            self._pl_event.record(side)
             ft, txs, tstat = self._text_features(True)
-        fi, vxs, vstat = self._image_features(img, True)
+        fi, vxs, vstat = self._image_features(img, True, wait_before_assemble=self._pl_event)
         main.wait_stream(side)
         logits = self._buf("head.logits", (B, C), F32)
         loss = loss_out if loss_out is not None else self._buf("head.loss", (1,), F32)

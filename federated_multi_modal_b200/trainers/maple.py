@@ -412,8 +412,13 @@ class MaPLe(TrainerX):
 
     def _step_kernels(self, img, lab):
         eng = self.model.engine
+        # input validity scan on the side branch (it only has to finish before the optimiser; forward_backward joins
+        # the side stream before the logits head)
+        side, cur = eng._side_stream(), torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.check_finite(img, self._flag)
         eng.forward_backward(img, lab, loss_out=self._readback[0:1])
-        ops.check_finite(img, self._flag)
         # device-side guard: a NaN/Inf image or loss skips the update (the reference raises before optim.step())
         norm = eng.sgd_step(0.0, hyper=self._hyper_dev, loss_dev=self._readback[0:1], flag_dev=self._flag)
         self._readback[1:2].copy_(norm)
