@@ -357,6 +357,84 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   store_frag_bf16(gk + D, ld, k0 + warp * 16, T, dv, 1.f, 1.f, lane);
 }
 
+
+// ============================================================================ backward, short sequences (T <= 32)
+// The text tower runs on T_eff ~ 10 positions: delta + dQ + dK/dV as three launches of 64-row tensor-core tiles are
+// three dependent launches of almost-empty tiles on a latency-bound side stream. One CTA per (sequence, head) does
+// the whole backward in fp32 out of shared memory instead: S = Q K^T, P = exp2(c S - lse), dP = dO V^T,
+// delta = rowsum(dO * O), dS = P * (dP - delta), dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO.
+constexpr int SMALL_T = 32, SMALL_THREADS = 128;
+template <bool CAUSAL>
+__global__ void __launch_bounds__(SMALL_THREADS)
+attn_bwd_small_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ d_out,
+                      const float* __restrict__ lse, bf16* __restrict__ dqkv, int T, int heads, float scale) {
+  extern __shared__ float sm_small[];
+  const int D = heads * HD, D3 = 3 * D;
+  const int h = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  float* sQ = sm_small;                // [T][HD + 1] (padded: a thread walks a row while its neighbours walk other rows)
+  float* sK = sQ + T * (HD + 1);
+  float* sV = sK + T * (HD + 1);
+  float* sdO = sV + T * (HD + 1);
+  float* sP = sdO + T * (HD + 1);      // [T][T]
+  float* sdS = sP + T * T;             // [T][T]
+  float* sDelta = sdS + T * T;         // [T]
+  float* sL = sDelta + T;              // [T]
+  pdl_trigger();
+  pdl_wait();
+  const bf16* base = qkv + (size_t)n * T * D3 + h * HD;
+  const bf16* ob = out + (size_t)n * T * D + h * HD;
+  const bf16* db = d_out + (size_t)n * T * D + h * HD;
+  for (int i = tid; i < T * (HD / 2); i += SMALL_THREADS) {
+    const int r = i / (HD / 2), c2 = (i % (HD / 2)) * 2;
+    const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + (size_t)r * D3 + c2));
+    const float2 k = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + (size_t)r * D3 + D + c2));
+    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + (size_t)r * D3 + 2 * D + c2));
+    const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(db + (size_t)r * D + c2));
+    float* d = sQ + r * (HD + 1) + c2; d[0] = q.x; d[1] = q.y;
+    d = sK + r * (HD + 1) + c2; d[0] = k.x; d[1] = k.y;
+    d = sV + r * (HD + 1) + c2; d[0] = v.x; d[1] = v.y;
+    d = sdO + r * (HD + 1) + c2; d[0] = g.x; d[1] = g.y;
+  }
+  // delta_i = <dO_i, O_i>: 4 lanes per row would be enough; a warp per row keeps it simple (T <= 32 rows, 4 warps)
+  for (int r = tid >> 5; r < T; r += SMALL_THREADS / 32) {
+    const int lane = tid & 31;
+    const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(ob + (size_t)r * D + 2 * lane));
+    const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(db + (size_t)r * D + 2 * lane));
+    const float s = warp_sum(o.x * g.x + o.y * g.y);
+    if (lane == 0) { sDelta[r] = s; sL[r] = lse[((size_t)n * heads + h) * T + r]; }
+  }
+  __syncthreads();
+  const float c = scale * kLog2e;
+  for (int e = tid; e < T * T; e += SMALL_THREADS) {
+    const int i = e / T, j = e % T;
+    const float* qi = sQ + i * (HD + 1);
+    const float* kj = sK + j * (HD + 1);
+    const float* gi = sdO + i * (HD + 1);
+    const float* vj = sV + j * (HD + 1);
+    float s = 0.f, dp = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < HD; ++d) { s = fmaf(qi[d], kj[d], s); dp = fmaf(gi[d], vj[d], dp); }
+    const bool ok = !CAUSAL || j <= i;
+    const float pr = ok ? exp2f(s * c - sL[i]) : 0.f;
+    sP[e] = pr;
+    sdS[e] = pr * (dp - sDelta[i]);
+  }
+  __syncthreads();
+  bf16* gbase = dqkv + (size_t)n * T * D3 + h * HD;
+  for (int e = tid; e < T * HD; e += SMALL_THREADS) {
+    const int r = e / HD, d = e % HD;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j < T; ++j) {
+      dq = fmaf(sdS[r * T + j], sK[j * (HD + 1) + d], dq);     // dQ_r += dS[r][j] K_j
+      dk = fmaf(sdS[j * T + r], sQ[j * (HD + 1) + d], dk);     // dK_r += dS[j][r] Q_j
+      dv = fmaf(sP[j * T + r], sdO[j * (HD + 1) + d], dv);     // dV_r += P[j][r] dO_j
+    }
+    gbase[(size_t)r * D3 + d] = __float2bfloat16_rn(dq * scale);
+    gbase[(size_t)r * D3 + D + d] = __float2bfloat16_rn(dk * scale);
+    gbase[(size_t)r * D3 + 2 * D + d] = __float2bfloat16_rn(dv);
+  }
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -389,6 +467,21 @@ extern "C" int mfk_attn_fwd(const void* qkv, void* out, float* lse, int N, int T
 extern "C" int mfk_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
                             void* dqkv, int N, int T, int heads, int causal, void* stream) {
   if (!qkv || !out || !d_out || !lse || !delta_ws || !dqkv || N <= 0 || T <= 0 || T > 256) return MFK_EARG;
+  if (T <= SMALL_T) {  // one launch: the whole backward of a (sequence, head) in one CTA (delta_ws is not used)
+    const size_t smem = sizeof(float) * (4 * (size_t)T * (HD + 1) + 2 * (size_t)T * T + 2 * (size_t)T);
+    cudaError_t e;
+    if (causal)
+      e = launch_pdl(attn_bwd_small_kernel<true>, dim3(heads, N), dim3(SMALL_THREADS), smem, ST(stream),
+                     static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), lse,
+                     static_cast<bf16*>(dqkv), T, heads, 0.125f);
+    else
+      e = launch_pdl(attn_bwd_small_kernel<false>, dim3(heads, N), dim3(SMALL_THREADS), smem, ST(stream),
+                     static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), lse,
+                     static_cast<bf16*>(dqkv), T, heads, 0.125f);
+    if (e != cudaSuccess) return (int)e;
+    MFK_CHECK_LAUNCH();
+    return MFK_OK;
+  }
   const int Tp = ((T + TILE - 1) / TILE) * TILE;
   const long long rows = (long long)N * T;
   const long long warps = rows * heads;

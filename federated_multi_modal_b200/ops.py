@@ -71,7 +71,7 @@ def attn_bwd(qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads, causal, impl: Op
         return
     use_tc = (TC_ATTN_MIN_T <= T <= 240) if impl is None else impl == "tc"
     call("mfk_attn_bwd_tc" if use_tc else "mfk_attn_bwd", qkv, out, d_out, lse, delta_ws, dqkv, N, T, heads,
-         int(causal), stream_ptr(), kernels=3)
+         int(causal), stream_ptr(), kernels=1 if (not use_tc and T <= 32) else 3)  # T <= 32: one fused small-T launch
 
 
 def layernorm_fwd(x, gamma, beta, *, rowidx=None, y_bf16=None, y_f32=None, x_save=None, mean=None, rstd=None,

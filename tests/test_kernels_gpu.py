@@ -148,7 +148,8 @@ def _attn_ref(qkv, N, T, heads, causal):
 
 @pytest.mark.parametrize("N,T,heads,causal", [(2, 199, 12, False), (3, 77, 8, True), (4, 16, 8, True),
                                               (2, 64, 2, False), (1, 256, 1, True), (5, 11, 8, True),
-                                              (32, 199, 12, False)])
+                                              (32, 199, 12, False), (3, 10, 8, False), (2, 32, 8, True),
+                                              (2, 33, 8, True)])  # T <= 32: one-launch small-T backward (text tower)
 @pytest.mark.parametrize("impl", ["mma", "tc", "fused"])
 def test_attention_fwd_bwd(N, T, heads, causal, impl):
     if impl == "fused" and causal:
