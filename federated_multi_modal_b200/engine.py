@@ -785,12 +785,17 @@ class MapleEngine:
                           g_out=vws["g"], dgamma=G["image_encoder.ln_pre.weight"] if ln_grads else None,
                           dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None)
         ops.prompt_splice_bwd(vws["g"], None, self.d_shared, B, self.Tv, self.Tv - n, n, True, False)
-        self._ln_reduce(self.vis)
-        main.wait_stream(side)
+        # tail: the grouped dgamma / dbeta reduction of the vision tower (20 us, small CTAs) runs on the by now idle side
+        # branch next to the prompt learner's backward instead of in front of it; both join before the optimiser
+        main.wait_stream(side)              # text backward (and its reduction) done: d(ctx), d(deep text prompts)
+        side.wait_stream(main)              # every vision LayerNorm backward has left its partials
+        with torch.cuda.stream(side):
+            self._ln_reduce(self.vis)
 
         # ---- prompt learner backward: dW, db and dx = dy W + d(prompt) for all projections in
         # two grouped launches (the problem table was built with the forward one)
         ops.linear_small_bwd_grouped(self._pl_table, n, max(self.vis.D, self.txt.D), max(self.vis.D, self.txt.D))
+        main.wait_stream(side)
         self.last = dict(image_features=fi, text_features=ft, dfi=dfi, dft=dft)
         return loss, logits
 
