@@ -4,7 +4,7 @@ import torch, bench
 from federated_multi_modal_b200 import engine as E
 
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
-def run(skip):
+def run(skip, only=None):
     t = bench.make_trainer(dev, graph=True)
     eng = t.model.engine
     if skip:
@@ -18,7 +18,8 @@ def run(skip):
                 if "b" not in cache: cache["b"] = orig_tb(tw, *a, **k)
                 return cache["b"]
             return orig_tb(tw, *a, **k)
-        eng._text_features, eng._tower_bwd = tf, tb
+        if only in (None, "fwd"): eng._text_features = tf
+        if only in (None, "bwd"): eng._tower_bwd = tb
     b = bench.host_batches(1, 32, 0)[0]
     img, lab = b["img"].to(dev), b["label"].to(dev)
     for _ in range(5): t.step_async(img, lab)
@@ -30,3 +31,5 @@ def run(skip):
     return s.elapsed_time(e) / 20
 print("with text tower   : %.3f ms/step" % run(False))
 print("text tower skipped: %.3f ms/step" % run(True))
+print("text FORWARD skipped only : %.3f ms/step" % run(True, "fwd"))
+print("text BACKWARD skipped only: %.3f ms/step" % run(True, "bwd"))
