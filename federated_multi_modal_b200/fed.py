@@ -8,7 +8,8 @@ Transports for the client tensors (flat fp32 arenas of the trainable parameters)
   "p2p"  — symmetric-memory buffers: every rank's reduce kernel loads the peers' rows straight over
            NVLink (peer pointers in the kernel's pointer table), i.e. transfer and weighted reduction are
            ONE kernel; a symmetric-memory barrier on each side orders it against the producers.
-  "p2p_sharded" — the all-reduce-shaped form of the same thing (opt-in, cfg.FED.TRANSPORT): rank r reduces only elements
+  "p2p_sharded" — the all-reduce-shaped form of the same thing (the default on NCCL since round 2; cfg.FED.TRANSPORT
+           selects another, cfg.FED.STRICT_TRANSPORT forbids the collective downgrade): rank r reduces only elements
            [r*n/W, (r+1)*n/W) of the K rows (same per-element order => bit-identical) and pushes the fp32 / fp16 result
            into every rank's output buffer with peer stores (`mfk_fedavg_reduce_scatter`): (W-1)/W * 10 bytes per
            element over NVLink instead of (W-1) * 4.

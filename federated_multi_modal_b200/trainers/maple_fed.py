@@ -81,7 +81,8 @@ class MaPLeFederated(TrainerX):
             self.clients.append(t)
         eng = self.clients[0].model.engine
         self.exchange = FedAvgExchange(eng.n_update, len(self.clients), self.device,
-                                       transport=_fed(self.cfg, "TRANSPORT", "auto"))
+                                       transport=_fed(self.cfg, "TRANSPORT", "auto"),
+                                       strict_transport=bool(_fed(self.cfg, "STRICT_TRANSPORT", False)))
         self.global_arena = eng.params[: eng.n_update].clone()
         self.global_weights = self.clients[0].model.state_dict()
         self._frozen_rounded = False
