@@ -105,7 +105,10 @@ class MaPLeFederated(TrainerX):
                 try:
                     for ep in range(trainer.epoch, trainer.max_epoch):
                         last = trainer.run_epoch(ep).get("avg_loss", 0.0)
-                except (RuntimeError, ValueError) as e:  # trainers/maple_fed.py:262-265
+                # the reference catches RuntimeError only (trainers/maple_fed.py:262-265): "NaN/Inf in total loss" drops
+                # the client for the round, while the ValueError of a NaN / Inf INPUT (check_tensor_validity,
+                # trainers/maple.py:525-535) escapes and ends the run; cfg.FED.DROP_ON_INPUT_ERROR also drops those
+                except ((RuntimeError, ValueError) if _fed(self.cfg, "DROP_ON_INPUT_ERROR", False) else RuntimeError) as e:
                     print(f"Client {trainer.client_id} failed training: {e}")
                     self.nan_stats["failed_clients"].append(trainer.client_id)
                     ok = False

@@ -255,3 +255,75 @@ def test_load_state_dict_reaches_frozen_tensors_and_failed_step_keeps_weights():
         assert torch.equal(eng.vis.w[11]["mlp.c_fc.w"], snap[2])
     out = t.forward_backward({"img": img, "label": lab})            # training continues normally afterwards
     assert out["loss"] > 0 and not torch.equal(eng.params, snap[0])
+
+
+def test_federated_failure_bookkeeping_and_weighted_mode():
+    """Round orchestration of trainers/maple_fed.py:228-303: a client whose local training raises is dropped from the
+    round (failed_clients), the average runs over the remaining clients only (divisor = their number, or their sample
+    count in the weighted mode); if every client fails the round is skipped and the previous global model stays."""
+    import contextlib, io
+    from federated_multi_modal_b200.trainers import Datum
+    C, K = 4, 3
+    names = synth.synthetic_classnames(C)
+    pool = synthetic_client_items(C, 3, seed=2, classnames=names)               # 12 images
+
+    def make(bad_clients, weighted, sizes=(4, 4, 4), poison=3.0e38, drop_on_input_error=False):
+        cfg = synth.make_cfg()
+        cfg.FED.DROP_ON_INPUT_ERROR = drop_on_input_error
+        cfg.FED.NUM_CLIENTS, cfg.FED.NUM_ROUNDS, cfg.FED.LOCAL_EPOCHS = K, 1, 1
+        cfg.FED.WEIGHTED = weighted
+        cfg.DATALOADER = synth._NS(TRAIN_X=synth._NS(BATCH_SIZE=2), TEST=synth._NS(BATCH_SIZE=4))
+        cfg.OUTPUT_DIR = ""
+        dms, off = [], 0
+        for k in range(K):
+            items = [Datum(impath=it.impath, label=it.label, classname=it.classname, img=it.img.clone())
+                     for it in pool[off:off + sizes[k]]]
+            off += sizes[k]
+            if k in bad_clients:
+                for it in items:
+                    it.img.fill_(poison)        # finite but overflowing: "NaN/Inf in total loss" (RuntimeError) every batch
+            dms.append(ClientDataManager(items, [], [], cfg))
+        fed = MaPLeFederated(cfg, client_data_managers=dms, classnames=names)
+        cap = {}
+        orig = fed._aggregate
+        def spy():
+            cap["rows"] = [r.clone().cpu() for r in fed.exchange.gather()]
+            cap["status"] = fed.exchange.status.cpu().clone()
+            return orig()
+        fed._aggregate = spy
+        return fed, cap
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        fed, cap = make({1}, weighted=False)
+        start = fed.global_arena.clone()
+        fed.train()
+    assert fed.nan_stats["failed_clients"] == [1] and fed.nan_stats["total_updates"] == 1
+    assert cap["status"][:, 0].tolist() == [1.0, 0.0, 1.0]
+    m32, m16 = fedavg_oracle([cap["rows"][0], cap["rows"][2]])
+    assert torch.equal(fed.last_mean_fp32.cpu(), m32) and torch.equal(fed.global_arena.cpu(), m16.float())
+    assert not torch.equal(fed.global_arena, start)
+    # the dropped client did not train (its update was rejected before the optimiser): its row is the broadcast model
+    assert torch.equal(cap["rows"][1], start.cpu())
+    # ---- weighted by sample count (north_star extension): 6 / 2 / 4 training images
+    with contextlib.redirect_stdout(io.StringIO()):
+        fed, cap = make(set(), weighted=True, sizes=(6, 2, 4))
+        fed.train()
+    assert cap["status"][:, 1].tolist() == [6.0, 2.0, 4.0]
+    m32, _ = fedavg_oracle(cap["rows"], [6.0, 2.0, 4.0])
+    assert torch.equal(fed.last_mean_fp32.cpu(), m32)
+    # ---- every client fails: round skipped, global model unchanged
+    with contextlib.redirect_stdout(io.StringIO()):
+        fed, cap = make({0, 1, 2}, weighted=False)
+        start = fed.global_arena.clone()
+        fed.train()
+    assert fed.nan_stats["skipped_rounds"] == 1 and fed.nan_stats["total_updates"] == 0
+    assert sorted(fed.nan_stats["failed_clients"]) == [0, 1, 2]
+    assert torch.equal(fed.global_arena, start)
+    # ---- a NaN INPUT raises ValueError, which the reference's round loop does not catch (only RuntimeError)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fed, cap = make({1}, weighted=False, poison=float("nan"))
+        with pytest.raises(ValueError, match="NaN values in input image"):
+            fed.train()
+        fed, cap = make({1}, weighted=False, poison=float("nan"), drop_on_input_error=True)   # opt-in: drop instead
+        fed.train()
+    assert fed.nan_stats["failed_clients"] == [1] and fed.nan_stats["total_updates"] == 1
