@@ -50,6 +50,9 @@ SIGNATURES = {
     "mfk_quickgelu_split_bf16x3": [P, P, I, I, P],
     "mfk_patch_im2col_f32": [P, P, I, I, P],
     "mfk_attn_fwd_f32": [P, P, I, I, I, I, P],
+    "mfk_attn_bwd_f32": [P, P, P, P, I, I, I, I, P],
+    "mfk_dquickgelu_mul_f32": [P, P, P, L, P],
+    "mfk_split_bf16x3_rhs": [P, P, I, I, P],
     "mfk_attn_rows_fwd": [P, P, P, P, I, I, I, I, P],
     "mfk_attn_rows_bwd": [P, P, P, P, P, I, I, I, I, P],
     "mfk_linear_small_fwd": [P, P, P, P, I, I, I, P],

@@ -1682,6 +1682,192 @@ extern "C" int mfk_attn_fwd_f32(const float* qkv, float* out, int N, int T, int 
 }
 
 // =====================================================================================================
+// fp32 attention BACKWARD of the fp32 training mode (cfg PREC = "fp32": the reference trains its fp32 model,
+// trainers/maple.py:438-439, 590). Same SIMT organisation as the forward above, two deterministic kernels:
+//   dq  kernel, CTA = (sequence, head, 32-query block), K and V of the head in smem: per query row the softmax is
+//       recomputed (row max, sum), dP_j = dO . V_j, delta = sum_j P_j dP_j, dS_j = P_j (dP_j - delta),
+//       dQ = sum_j dS_j K_j / 8; it also leaves lse (natural log) and delta of every row in scratch;
+//   dkv kernel, CTA = (sequence, head, 32-key block), Q and dO of the head in smem: per key row
+//       P_i = exp(q_i . k / 8 - lse_i), dS_i = P_i (dO_i . v - delta_i), dV = sum_i P_i dO_i, dK = sum_i dS_i q_i / 8.
+// Sums run in index order inside one warp: bit-reproducible.
+namespace {
+template <bool CAUSAL>
+__global__ void __launch_bounds__(F32_WARPS * 32)
+attn_bwd_dq_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, float* __restrict__ dqkv,
+                       float* __restrict__ lse, float* __restrict__ delta, int T, int heads) {
+  extern __shared__ float sm_f32[];
+  const int D = heads * HD;
+  float* sK = sm_f32;                      // [T][65]
+  float* sV = sK + (size_t)T * 65;         // [T][65]
+  float* sP = sV + (size_t)T * 65;         // [F32_WARPS][2][T]: probabilities and dP of the row a warp works on
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * F32_QBLK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = qkv + (size_t)n * T * 3 * D + h * HD;
+  const int kend = CAUSAL ? min(T, q0 + F32_QBLK) : T;
+  for (int i = threadIdx.x; i < kend * HD; i += blockDim.x) {
+    const int r = i / HD, c = i % HD;
+    sK[r * 65 + c] = base[(size_t)r * 3 * D + D + c];
+    sV[r * 65 + c] = base[(size_t)r * 3 * D + 2 * D + c];
+  }
+  __syncthreads();
+  float* myP = sP + (size_t)warp * 2 * T;
+  float* myDP = myP + T;
+  for (int qi = q0 + warp; qi < min(T, q0 + F32_QBLK); qi += F32_WARPS) {
+    const float* qrow = base + (size_t)qi * 3 * D;
+    const float q_lo = qrow[lane], q_hi = qrow[lane + 32];
+    const float* dorow = d_out + ((size_t)n * T + qi) * D + h * HD;
+    const float do_lo = dorow[lane], do_hi = dorow[lane + 32];
+    const int kmax = CAUSAL ? qi + 1 : T;
+    float mx = -INFINITY;
+    for (int k0 = 0; k0 < kmax; k0 += 32) {
+      const int k = k0 + lane;
+      const int kk = min(k, kmax - 1);
+      float a = 0.f, b = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < 32; ++c) {
+        a = fmaf(__shfl_sync(0xffffffffu, q_lo, c), sK[kk * 65 + c], a);
+        a = fmaf(__shfl_sync(0xffffffffu, q_hi, c), sK[kk * 65 + 32 + c], a);
+        b = fmaf(__shfl_sync(0xffffffffu, do_lo, c), sV[kk * 65 + c], b);
+        b = fmaf(__shfl_sync(0xffffffffu, do_hi, c), sV[kk * 65 + 32 + c], b);
+      }
+      const float sc = k < kmax ? a * 0.125f : -INFINITY;
+      if (k < kmax) {
+        myP[k] = sc;
+        myDP[k] = b;
+      }
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    float l = 0.f;
+    for (int k = lane; k < kmax; k += 32) {
+      const float e = expf(myP[k] - mx);
+      myP[k] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    const float inv = 1.f / l;
+    float dl = 0.f;
+    for (int k = lane; k < kmax; k += 32) {  // each lane revisits the entries it wrote itself
+      const float pn = myP[k] * inv;
+      myP[k] = pn;
+      dl = fmaf(pn, myDP[k], dl);
+    }
+    dl = warp_sum(dl);
+    __syncwarp();
+    float dq_lo = 0.f, dq_hi = 0.f;
+    for (int k = 0; k < kmax; ++k) {
+      const float ds = myP[k] * (myDP[k] - dl);
+      dq_lo = fmaf(ds, sK[k * 65 + lane], dq_lo);
+      dq_hi = fmaf(ds, sK[k * 65 + 32 + lane], dq_hi);
+    }
+    float* dqrow = dqkv + ((size_t)n * T + qi) * 3 * D + h * HD;
+    dqrow[lane] = dq_lo * 0.125f;
+    dqrow[lane + 32] = dq_hi * 0.125f;
+    if (lane == 0) {
+      lse[((size_t)n * heads + h) * T + qi] = mx + logf(l);
+      delta[((size_t)n * heads + h) * T + qi] = dl;
+    }
+    __syncwarp();
+  }
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(F32_WARPS * 32)
+attn_bwd_dkv_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, float* __restrict__ dqkv,
+                        const float* __restrict__ lse, const float* __restrict__ delta, int T, int heads) {
+  extern __shared__ float sm_f32[];
+  const int D = heads * HD;
+  float* sQ = sm_f32;                      // [T][65]
+  float* sdO = sQ + (size_t)T * 65;        // [T][65]
+  float* sL = sdO + (size_t)T * 65;        // [T] lse
+  float* sDl = sL + T;                     // [T] delta
+  float* sP = sDl + T;                     // [F32_WARPS][2][T]
+  const int n = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * F32_QBLK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = qkv + (size_t)n * T * 3 * D + h * HD;
+  const int qbeg = CAUSAL ? j0 : 0;  // queries before the block's first key see none of its keys
+  for (int i = threadIdx.x + qbeg * HD; i < T * HD; i += blockDim.x) {
+    const int r = i / HD, c = i % HD;
+    sQ[r * 65 + c] = base[(size_t)r * 3 * D + c];
+    sdO[r * 65 + c] = d_out[((size_t)n * T + r) * D + h * HD + c];
+  }
+  for (int i = threadIdx.x + qbeg; i < T; i += blockDim.x) {
+    sL[i] = lse[((size_t)n * heads + h) * T + i];
+    sDl[i] = delta[((size_t)n * heads + h) * T + i];
+  }
+  __syncthreads();
+  float* myP = sP + (size_t)warp * 2 * T;
+  float* myDS = myP + T;
+  for (int kj = j0 + warp; kj < min(T, j0 + F32_QBLK); kj += F32_WARPS) {
+    const float* krow = base + (size_t)kj * 3 * D + D;
+    const float k_lo = krow[lane], k_hi = krow[lane + 32];
+    const float v_lo = krow[D + lane], v_hi = krow[D + lane + 32];
+    const int imin = CAUSAL ? kj : 0;
+    for (int i0 = imin; i0 < T; i0 += 32) {
+      const int i = i0 + lane;
+      const int ii = min(i, T - 1);
+      float a = 0.f, b = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < 32; ++c) {
+        a = fmaf(__shfl_sync(0xffffffffu, k_lo, c), sQ[ii * 65 + c], a);
+        a = fmaf(__shfl_sync(0xffffffffu, k_hi, c), sQ[ii * 65 + 32 + c], a);
+        b = fmaf(__shfl_sync(0xffffffffu, v_lo, c), sdO[ii * 65 + c], b);
+        b = fmaf(__shfl_sync(0xffffffffu, v_hi, c), sdO[ii * 65 + 32 + c], b);
+      }
+      if (i < T) {
+        const float pr = expf(a * 0.125f - sL[i]);
+        myP[i] = pr;
+        myDS[i] = pr * (b - sDl[i]);
+      }
+    }
+    __syncwarp();
+    float dv_lo = 0.f, dv_hi = 0.f, dk_lo = 0.f, dk_hi = 0.f;
+    for (int i = imin; i < T; ++i) {
+      const float pr = myP[i], ds = myDS[i];
+      dv_lo = fmaf(pr, sdO[i * 65 + lane], dv_lo);
+      dv_hi = fmaf(pr, sdO[i * 65 + 32 + lane], dv_hi);
+      dk_lo = fmaf(ds, sQ[i * 65 + lane], dk_lo);
+      dk_hi = fmaf(ds, sQ[i * 65 + 32 + lane], dk_hi);
+    }
+    float* dkrow = dqkv + ((size_t)n * T + kj) * 3 * D + D + h * HD;
+    dkrow[lane] = dk_lo * 0.125f;
+    dkrow[lane + 32] = dk_hi * 0.125f;
+    dkrow[D + lane] = dv_lo;
+    dkrow[D + lane + 32] = dv_hi;
+    __syncwarp();
+  }
+}
+}  // namespace
+
+extern "C" int mfk_attn_bwd_f32(const float* qkv, const float* d_out, float* dqkv, float* stat_ws, int N, int T,
+                                int heads, int causal, void* stream) {
+  if (!qkv || !d_out || !dqkv || !stat_ws || N <= 0 || T <= 0 || T > 256 || heads <= 0) return MFK_EARG;
+  const size_t smem_dq = ((size_t)2 * T * 65 + (size_t)F32_WARPS * 2 * T) * sizeof(float);
+  const size_t smem_dkv = ((size_t)2 * T * 65 + 2 * (size_t)T + (size_t)F32_WARPS * 2 * T) * sizeof(float);
+  float* lse = stat_ws;
+  float* delta = stat_ws + (size_t)N * heads * T;
+  dim3 grid((T + F32_QBLK - 1) / F32_QBLK, heads, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+#define MFK_ATTN_BWD_F32(C_)                                                                                          \
+  e = cudaFuncSetAttribute(attn_bwd_dq_f32_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq);    \
+  if (e != cudaSuccess) return (int)e;                                                                                \
+  e = cudaFuncSetAttribute(attn_bwd_dkv_f32_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv);  \
+  if (e != cudaSuccess) return (int)e;                                                                                \
+  attn_bwd_dq_f32_kernel<C_><<<grid, F32_WARPS * 32, smem_dq, st>>>(qkv, d_out, dqkv, lse, delta, T, heads);          \
+  attn_bwd_dkv_f32_kernel<C_><<<grid, F32_WARPS * 32, smem_dkv, st>>>(qkv, d_out, dqkv, lse, delta, T, heads);
+  if (causal) {
+    MFK_ATTN_BWD_F32(true)
+  } else {
+    MFK_ATTN_BWD_F32(false)
+  }
+#undef MFK_ATTN_BWD_F32
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+// =====================================================================================================
 // Single-query attention for the LAST block of a tower: only one row per sequence (CLS / EOT) of the block output
 // is consumed (clip/model.py:567, trainers/maple.py:72-76), so the attention core is needed for that query row
 // only — Q of one row against K, V of the whole sequence — and so is its backward: dQ lives on that row, dK / dV are

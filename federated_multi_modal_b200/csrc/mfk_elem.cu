@@ -482,6 +482,30 @@ __global__ void quickgelu_split_bf16x3_kernel(const float* __restrict__ u, bf16*
   o[D + c] = lo;
   o[2 * D + c] = hi;
 }
+// The B-side packing of the split-precision product for ACTIVATIONS: out[r] = [hi | hi | lo]. A wgrad
+// dW = dY^T X of the fp32 training mode contracts over the rows: a [rows, 3D] split buffer read as [3 rows, D]
+// (row 3r + j = part j of row r) pairs [hi | lo | hi] of one operand with [hi | hi | lo] of the other.
+__global__ void split_bf16x3_rhs_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * D) return;
+  const int r = (int)(i / D), c = (int)(i % D);
+  const float v = x[i];
+  const bf16 hi = __float2bfloat16_rn(v);
+  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = out + (size_t)r * 3 * D;
+  o[c] = hi;
+  o[D + c] = hi;
+  o[2 * D + c] = lo;
+}
+// Backward of QuickGELU in fp32 (exact sigmoid): du = dact * s (1 + 1.702 u (1 - s)), s = sigmoid(1.702 u).
+__global__ void dquickgelu_mul_f32_kernel(const float* __restrict__ dact, const float* __restrict__ u,
+                                          float* __restrict__ du, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = u[i];
+  const float s = 1.0f / (1.0f + expf(-1.702f * x));
+  du[i] = dact[i] * (s * (1.0f + 1.702f * x * (1.0f - s)));
+}
 // im2col of the 16x16 / stride-16 patch embedding kept in fp32 (fp32 mode: split into bf16x3 afterwards)
 __global__ void im2col16_f32_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int S) {
   const int G = S / 16;
@@ -1007,6 +1031,21 @@ extern "C" int mfk_quickgelu_split_bf16x3(const float* u, void* out_bf16, int ro
   const long long n = (long long)rows * D;
   quickgelu_split_bf16x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(u, static_cast<bf16*>(out_bf16),
                                                                                    rows, D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_split_bf16x3_rhs(const float* x, void* out_bf16, int rows, int D, void* stream) {
+  if (!x || !out_bf16 || rows <= 0 || D <= 0) return MFK_EARG;
+  const long long n = (long long)rows * D;
+  split_bf16x3_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, static_cast<bf16*>(out_bf16), rows, D);
+  MFK_CHECK_LAUNCH();
+  return MFK_OK;
+}
+
+extern "C" int mfk_dquickgelu_mul_f32(const float* dact, const float* u, float* du, long long n, void* stream) {
+  if (!dact || !u || !du || n <= 0) return MFK_EARG;
+  dquickgelu_mul_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(dact, u, du, n);
   MFK_CHECK_LAUNCH();
   return MFK_OK;
 }

@@ -89,6 +89,7 @@ class MapleEngine:
         self.eval_graph = os.environ.get("MFK_EVAL_GRAPH", "1") != "0"
         self.eval_text_f32 = os.environ.get("MFK_EVAL_TEXT", "fp32") != "bf16"
         self.mom_initialized = False
+        self.train_precision = "bf16"  # "fp32": forward_backward runs the split-operand fp32 training mode
         self.repack_trainable()
 
     # ------------------------------------------------------------------ parameters
@@ -700,6 +701,192 @@ class MapleEngine:
         ops.head_forward_backward(fi, ft, self.logit_scale, None, out, None, None, None, ws)
         return out
 
+    # ------------------------------------------------------------------ fp32 mode: training step
+    # cfg.TRAINER.MAPLE.PREC = "fp32": the reference calls clip_model.float() and trains the fp32 model
+    # (trainers/maple.py:438-439, 590). Same schedule as the bf16 step, with every contraction as a split-operand
+    # (bf16x3) GEMM on the tcgen05 kernel — forward, dgrad and the wgrads of resblocks.11 — and fp32 LayerNorm,
+    # attention, QuickGELU and residual stream in between. The last block runs in full (no consumed-row shortcut):
+    # this is the parity mode (gradients within 1e-3 of the reference's fp32 autograd), not the fast path.
+    def _w3T(self, tw: _Tower, l: int, lin: str) -> torch.Tensor:
+        """[K, 3N] hi|hi|lo split of W^T: the B operand of the fp32-mode dgrad GEMM dX = dY W."""
+        w = tw.w[l]
+        key = lin + ".w3T"
+        if key not in w or lin + ".master" in w:
+            src = w[lin + ".master"] if lin + ".master" in w else self._frozen_f32(tw, l, lin)
+            w[key] = self._split_b(src.t())
+        return w[key]
+
+    def _f32_train_bufs(self, tw: _Tower, N: int, T: int):
+        tw.N, tw.T, tw.M = N, T, N * T
+        M, D, L = tw.M, tw.D, tw.L
+        b = lambda n, s, d=F32: self._buf(f"{tw.name}.f32t.{n}", s, d)
+        S = dict(x1=b("x1", (L + 1, M, D)), x2=b("x2", (L, M, D)), qkv=b("qkv", (L, M, 3 * D)),
+                 att=b("att", (L, M, D)), u=b("u", (L, M, 4 * D)), stat=b("stat", (L, 4, M)),
+                 h1=b("h1", (M, D)), h2=b("h2", (M, D)), g=b("g", (M, D)), g_r=b("g_r", (N, D)),
+                 dact=b("dact", (M, 4 * D)), du=b("du", (M, 4 * D)), dh=b("dh", (M, D)), dqkv=b("dqkv", (M, 3 * D)),
+                 attn_ws=b("attn_ws", (2 * N * tw.heads * T,)), rhs=b("rhs", (M, 3 * D), BF16),
+                 lnp_all=b("lnp_all", (2 * L + 3, 2 * D * ops.ln_bwd_ctas(M))), csum=b("csum", (32 * 4 * D,)))
+        tw.ws = S  # _ln_bwd / _ln_reduce take their partial slots from tw.ws["lnp_all"]
+        return S
+
+    def _block_fwd_f32_train(self, tw: _Tower, l: int, splice=None):
+        S, w, M, D = tw.ws, tw.w[l], tw.M, tw.D
+        nm = f"{tw.name}.f32t."
+        x1, x1n, x2, st = S["x1"][l], S["x1"][l + 1], S["x2"][l], S["stat"][l]
+        ops.layernorm_fwd(x1, w["ln_1.g"], w["ln_1.b"], y_f32=S["h1"], mean=st[0], rstd=st[1], splice=splice)
+        ops.gemm(self._split_a(S["h1"], nm + "a3"), self._w3(tw, l, "attn.in_proj"), bias=w["attn.in_proj.b"],
+                 out_f32=S["qkv"][l])
+        ops.attn_fwd_f32(S["qkv"][l], S["att"][l], tw.N, tw.T, tw.heads, tw.causal)
+        ops.gemm(self._split_a(S["att"][l], nm + "a3"), self._w3(tw, l, "attn.out_proj"), bias=w["attn.out_proj.b"],
+                 residual=x1, out_f32=x2)
+        ops.layernorm_fwd(x2, w["ln_2.g"], w["ln_2.b"], y_f32=S["h2"], mean=st[2], rstd=st[3])
+        ops.gemm(self._split_a(S["h2"], nm + "a3"), self._w3(tw, l, "mlp.c_fc"), bias=w["mlp.c_fc.b"],
+                 out_f32=S["u"][l])
+        act3 = self._buf(nm + "act3", (M, 12 * D), BF16)
+        ops.quickgelu_split_bf16x3(S["u"][l], act3)
+        ops.gemm(act3, self._w3(tw, l, "mlp.c_proj"), bias=w["mlp.c_proj.b"], residual=x2, out_f32=x1n)
+
+    def _block_bwd_f32(self, tw: _Tower, l: int, splice_grad=None):
+        """In / out: tw.ws["g"] = gradient at the block output / input (fp32). Mirrors _block_bwd."""
+        S, w, M, D = tw.ws, tw.w[l], tw.M, tw.D
+        nm = f"{tw.name}.f32t."
+        g, st, G = S["g"], S["stat"][l], self.g
+        pre = f"{tw.name}.transformer.resblocks.{l}."
+        wg = self.wgrad_last and l == tw.L - 1
+        ln_grads = self.trainable == "reference"
+        rows3 = lambda t: t.view(3 * M, t.shape[1] // 3)  # [M, 3K] split buffer read as [3M, K]
+        # ---- MLP branch
+        g3 = self._split_a(g, nm + "g3")
+        ops.gemm(g3, self._w3T(tw, l, "mlp.c_proj"), out_f32=S["dact"])
+        if wg:
+            act3 = self._buf(nm + "act3", (M, 12 * D), BF16)
+            ops.quickgelu_split_bf16x3(S["u"][l], act3)
+            ops.split_bf16x3_rhs(g, S["rhs"])
+            ops.gemm_at_b(rows3(S["rhs"]), rows3(act3), G[pre + "mlp.c_proj.weight"])
+            ops.colsum(g, G[pre + "mlp.c_proj.bias"], S["csum"])
+        ops.dquickgelu_mul_f32(S["dact"], S["u"][l], S["du"])
+        du3 = self._split_a(S["du"], nm + "du3")
+        ops.gemm(du3, self._w3T(tw, l, "mlp.c_fc"), out_f32=S["dh"])
+        if wg:
+            ops.split_bf16x3_rhs(S["h2"], S["rhs"])
+            ops.gemm_at_b(rows3(du3), rows3(S["rhs"]), G[pre + "mlp.c_fc.weight"])
+            ops.colsum(S["du"], G[pre + "mlp.c_fc.bias"], S["csum"])
+        self._ln_bwd(tw, S["dh"], S["x2"][l], st[2], st[3], w["ln_2.g"], g_in=g, g_out=g,
+                     dgamma=G[pre + "ln_2.weight"] if ln_grads else None,
+                     dbeta=G[pre + "ln_2.bias"] if ln_grads else None)
+        # ---- attention branch
+        g3 = self._split_a(g, nm + "g3")
+        da = S["dh"]
+        ops.gemm(g3, self._w3T(tw, l, "attn.out_proj"), out_f32=da)
+        if wg:
+            ops.split_bf16x3_rhs(g, S["rhs"])
+            ops.gemm_at_b(rows3(S["rhs"]), rows3(self._split_a(S["att"][l], nm + "a3")),
+                          G[pre + "attn.out_proj.weight"])
+            ops.colsum(g, G[pre + "attn.out_proj.bias"], S["csum"])
+        ops.attn_bwd_f32(S["qkv"][l], da, S["dqkv"], S["attn_ws"], tw.N, tw.T, tw.heads, tw.causal)
+        dq3 = self._split_a(S["dqkv"], nm + "dq3")
+        ops.gemm(dq3, self._w3T(tw, l, "attn.in_proj"), out_f32=S["dh"])
+        if wg:
+            ops.split_bf16x3_rhs(S["h1"], S["rhs"])
+            ops.gemm_at_b(rows3(dq3), rows3(S["rhs"]), G[pre + "attn.in_proj_weight"])
+            ops.colsum(S["dqkv"], G[pre + "attn.in_proj_bias"], S["csum"])
+        self._ln_bwd(tw, S["dh"], S["x1"][l], st[0], st[1], w["ln_1.g"], g_in=g, g_out=g,
+                     dgamma=G[pre + "ln_1.weight"] if ln_grads else None,
+                     dbeta=G[pre + "ln_1.bias"] if ln_grads else None, splice_grad=splice_grad)
+
+    def _tower_fwd_f32_train(self, tw: _Tower, deep, row0: int, rows, ln_g, ln_b, projT, name: str):
+        for l in range(tw.L):
+            splice = (deep[l - 1], tw.T, row0, self.n) if (l >= 1 and (l - 1) < len(deep)) else None
+            self._block_fwd_f32_train(tw, l, splice)
+        return self._features(tw, tw.ws["x1"][tw.L], None, ln_g, ln_b, projT, name, tw.N, True, rowidx=rows)
+
+    def _tower_bwd_f32(self, tw: _Tower, dfeat, proj3, xs, stat, rows, lnname: str, deep_row0: int, name: str):
+        """d(features) -> gradient at the tower's (post-embedding) input, left in tw.ws["g"]; fills the deep-prompt
+        gradients of this tower (_dprompt_all). Mirrors _tower_bwd."""
+        p, G, n, nd = self.p, self.g, self.n, self.J - 1
+        ln_grads = self.trainable == "reference"
+        S, D, R = tw.ws, tw.D, tw.N
+        dy = self._buf(name + ".dy", (R, D), F32)
+        ops.gemm(self._split_a(dfeat, name + ".df3"), proj3, out_f32=dy)
+        self._ln_bwd(tw, dy, xs, stat[0], stat[1], p[lnname + ".weight"], g_out=S["g_r"],
+                     dgamma=G[lnname + ".weight"] if ln_grads else None,
+                     dbeta=G[lnname + ".bias"] if ln_grads else None, M=R)
+        ops.scatter_rows_dense(S["g_r"], rows, S["g"], tw.N, tw.T)
+        ns = max(0, min(nd, tw.L - 1))
+        gp = self._buf(f"{tw.name}.gprompt", (max(ns, 1), tw.N * n, D), F32)
+        dp_all = self._dprompt_all(tw)
+        for l in reversed(range(tw.L)):
+            sg = (gp[l - 1], tw.T, deep_row0, n) if 1 <= l <= ns else None
+            self._block_bwd_f32(tw, l, splice_grad=sg)
+        if ns > 0:
+            ops.prompt_splice_bwd_batched(gp[:ns], dp_all[:ns], tw.N, n, 0, n, True)
+        if ns < nd:
+            dp_all[ns:].zero_()
+
+    @torch.no_grad()
+    def forward_backward_f32(self, img: torch.Tensor, label: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
+        """forward_backward in the fp32 mode (same contract: fills ``self.g``, returns (loss[1], logits[B, C]))."""
+        assert img.is_cuda and img.dtype == F32 and label.is_cuda and label.dtype == torch.int64
+        B, C, n = img.shape[0], self.C, self.n
+        p, G = self.p, self.g
+        ln_grads = self.trainable == "reference"
+        self._text_cache_valid = False
+        for tw in (self.vis, self.txt):
+            tw.ln_slot, tw.ln_pending = 0, []
+        self._prompt_learner_fwd()
+        if getattr(self, "_proj3", None) is None:  # [D, 3E] splits of the two projections (B operands of their dgrads)
+            self._proj3 = (self._split_b(self._sd_src["image_encoder.proj"].to(self.dev, F32)),
+                           self._split_b(self._sd_src["text_encoder.text_projection"].to(self.dev, F32)))
+        # ---- text tower forward
+        tt = self.txt
+        St = self._f32_train_bufs(tt, C, self.Te)
+        ops.text_assemble(self.prefix, p["prompt_learner.ctx"], self.suffix, self.tpos, St["x1"][0], C, self.Te, n,
+                          self.Tfull)
+        self.txt_rows = self.eot_rows
+        ft, txs, tstat = self._tower_fwd_f32_train(tt, self.deep_text, 1, self.eot_rows,
+                                                   p["text_encoder.ln_final.weight"], p["text_encoder.ln_final.bias"],
+                                                   self.tproj_T, "txt32t")
+        # ---- vision tower forward
+        tv = self.vis
+        Sv = self._f32_train_bufs(tv, B, self.Tv)
+        colf = self._buf("vis.f32.col", (B * self.P, 3 * self.patch * self.patch), F32)
+        tok = self._buf("vis.f32.tok", (B * self.P, tv.D), F32)
+        ops.patch_im2col_f32(img, colf)
+        if getattr(self, "_conv_w3", None) is None:
+            self._conv_w3 = self._split_b(self._sd_src["image_encoder.conv1.weight"].to(self.dev, F32).reshape(tv.D, -1))
+        ops.gemm(self._split_a(colf, "vis.f32.col3"), self._conv_w3, out_f32=tok)
+        x0 = self._buf("vis.f32t.x0", (tv.M, tv.D), F32)
+        st0 = self._buf("vis.f32t.st0", (2, tv.M), F32)
+        ops.vis_assemble_lnpre(tok, self.cls, self.vpos, self.shared, p["image_encoder.ln_pre.weight"],
+                               p["image_encoder.ln_pre.bias"], x0, Sv["x1"][0], st0[0], st0[1], B, self.Tv, n)
+        key = f"cls_rows{B}"
+        if key not in self._bufs:
+            self._bufs[key] = (torch.arange(B, device=self.dev, dtype=torch.int32) * self.Tv).contiguous()
+        self.cls_rows = self._bufs[key]
+        fi, vxs, vstat = self._tower_fwd_f32_train(tv, self.deep_vis, self.Tv - n, self.cls_rows,
+                                                   p["image_encoder.ln_post.weight"], p["image_encoder.ln_post.bias"],
+                                                   self.vproj_T, "vis32t")
+        # ---- head
+        logits = self._buf("head.logits", (B, C), F32)
+        loss = loss_out if loss_out is not None else self._buf("head.loss", (1,), F32)
+        dfi, dft = self._buf("head.dfi", (B, self.E), F32), self._buf("head.dft", (C, self.E), F32)
+        hws = self._buf("head.ws", (ops.head_workspace_floats(B, C, self.E),), F32)
+        ops.head_forward_backward(fi, ft, self.logit_scale, label, logits, loss, dfi, dft, hws)
+        # ---- backward: text, then vision (one stream; the towers' workspaces are separate)
+        self._tower_bwd_f32(tt, dft, self._proj3[1], txs, tstat, self.eot_rows, "text_encoder.ln_final", 1, "txt32t")
+        ops.prompt_splice_bwd(St["g"], None, self.d_ctx_t, C, self.Te, 1, n, False, False)
+        self._ln_reduce(tt)
+        self._tower_bwd_f32(tv, dfi, self._proj3[0], vxs, vstat, self.cls_rows, "image_encoder.ln_post", self.Tv - n,
+                            "vis32t")
+        self._ln_bwd(tv, Sv["g"], x0, st0[0], st0[1], p["image_encoder.ln_pre.weight"], g_out=Sv["g"],
+                     dgamma=G["image_encoder.ln_pre.weight"] if ln_grads else None,
+                     dbeta=G["image_encoder.ln_pre.bias"] if ln_grads else None)
+        ops.prompt_splice_bwd(Sv["g"], None, self.d_shared, B, self.Tv, self.Tv - n, n, True, False)
+        self._ln_reduce(tv)
+        ops.linear_small_bwd_grouped(self._pl_table, n, max(self.vis.D, self.txt.D), max(self.vis.D, self.txt.D))
+        self.last = dict(image_features=fi, text_features=ft, dfi=dfi, dft=dft)
+        return loss, logits
+
     def last_image_features(self) -> torch.Tensor:
         return self._last_fi.clone()
 
@@ -742,10 +929,15 @@ class MapleEngine:
 
     # ------------------------------------------------------------------ public: training step
     @torch.no_grad()
-    def forward_backward(self, img: torch.Tensor, label: torch.Tensor, loss_out: Optional[torch.Tensor] = None):
+    def forward_backward(self, img: torch.Tensor, label: torch.Tensor, loss_out: Optional[torch.Tensor] = None,
+                         precision: Optional[str] = None):
         """Forward + backward of one batch. Fills ``self.g[name]`` (fp32 arena) for every trainable tensor and
-        returns (loss[1], logits[B,C]) device tensors. No host synchronisation."""
+        returns (loss[1], logits[B,C]) device tensors. No host synchronisation.
+        ``precision`` (default: ``self.train_precision``, "bf16"): "fp32" runs the split-operand fp32 training mode
+        (forward_backward_f32; cfg PREC = "fp32" of the reference, trainers/maple.py:438-439)."""
         assert img.is_cuda and img.dtype == F32 and label.is_cuda and label.dtype == torch.int64
+        if (precision or self.train_precision) == "fp32":
+            return self.forward_backward_f32(img, label, loss_out)
         B, C, n, nd = img.shape[0], self.C, self.n, self.J - 1
         p, G = self.p, self.g
         self._text_cache_valid = False
@@ -864,6 +1056,7 @@ class MapleEngine:
                 w = tw.w[l]
                 for lin in _LIN:
                     w.pop(lin + ".w3", None)
+                    w.pop(lin + ".w3T", None)
                     if lin + ".master" in w:
                         continue  # lives in the arena (copied above); bf16 copies come from repack_trainable()
                     wk, bk = _lin_keys(lin)
@@ -884,6 +1077,7 @@ class MapleEngine:
         self.tproj.copy_(tp)
         self.tproj_T.copy_(self._split_b(tp.t()))
         self._conv_w3 = None
+        self._proj3 = None
         self._sd_src.update(sd)  # references (fp32 mode re-reads the exact frozen weights)
         self.repack_trainable()  # also invalidates the text-feature cache
 

@@ -213,6 +213,24 @@ def attn_fwd_f32(qkv, out, N, T, heads, causal):
     call("mfk_attn_fwd_f32", qkv, out, N, T, heads, int(causal), stream_ptr())
 
 
+def attn_bwd_f32(qkv, d_out, dqkv, stat_ws, N, T, heads, causal):
+    """fp32 training mode: dqkv fp32 [N*T, 3D] from d_out fp32 [N*T, D]; stat_ws: 2*N*heads*T floats."""
+    _chk(qkv, F32, "qkv"); _chk(d_out, F32, "d_out"); _chk(dqkv, F32, "dqkv"); _chk(stat_ws, F32, "stat_ws")
+    assert stat_ws.numel() >= 2 * N * heads * T
+    call("mfk_attn_bwd_f32", qkv, d_out, dqkv, stat_ws, N, T, heads, int(causal), stream_ptr(), kernels=2)
+
+
+def dquickgelu_mul_f32(dact, u, du):
+    _chk(dact, F32, "dact"); _chk(u, F32, "u"); _chk(du, F32, "du")
+    call("mfk_dquickgelu_mul_f32", dact, u, du, u.numel(), stream_ptr())
+
+
+def split_bf16x3_rhs(x, out):
+    """out[rows, 3D] = [hi | hi | lo] (B-side packing; split_bf16x3 gives the A-side [hi | lo | hi])."""
+    _chk(x, F32, "x"); _chk(out, BF16, "out")
+    call("mfk_split_bf16x3_rhs", x, out, x.shape[0], x.shape[1], stream_ptr())
+
+
 def linear_small_fwd(x, W, b, y):
     call("mfk_linear_small_fwd", x, W, b, y, x.shape[0], W.shape[0], W.shape[1], stream_ptr())
 

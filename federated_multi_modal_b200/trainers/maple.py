@@ -205,6 +205,9 @@ class CustomCLIP(nn.Module):
                                   depth=self.prompt_learner.compound_prompts_depth, device=str(dev),
                                   trainable="reference" if ref_set else "prompt_only",
                                   text_truncate=self.text_truncate, share_from=share_from)
+        # PREC == "fp32": the reference trains the fp32 model (trainers/maple.py:438-439) -> fp32 training mode
+        if str(getattr(self._cfg.TRAINER.MAPLE, "PREC", "bf16")) == "fp32":
+            self.engine.train_precision = "fp32"
         self._grad_params = [(n, p) for n, p in named.items() if n in self.engine.p and p.requires_grad]
         self._versions = self._param_versions()
         return self.engine
@@ -269,9 +272,10 @@ class CustomCLIP(nn.Module):
             if not bool(torch.isfinite(loss)):
                 raise RuntimeError("NaN/Inf in total loss")  # trainers/maple.py:375-376
             return loss
-        # PREC == "fp32" (trainers/maple.py:438-439 calls clip_model.float()): inference runs the engine's fp32 mode
-        # (bf16x3 split-operand GEMMs, fp32 everything else; logits within 1e-3 of the reference's fp32 path).
-        # Training always uses the bf16 tensor-core path with fp32 master weights.
+        # PREC == "fp32" (trainers/maple.py:438-439 calls clip_model.float()): inference AND training run the engine's
+        # fp32 mode (bf16x3 split-operand GEMMs, fp32 everything else; logits within 1e-3 of the reference's fp32
+        # path, gradients within 1e-3 of its fp32 autograd). Every other PREC uses the bf16 tensor-core path with
+        # fp32 master weights.
         prec = "fp32" if str(getattr(self._cfg.TRAINER.MAPLE, "PREC", "bf16")) == "fp32" else "bf16"
         logits = eng.logits(image, precision=prec)
         if return_feature:  # kept for signature compatibility with upstream MaPLe
@@ -344,6 +348,8 @@ class MaPLe(TrainerX):
                     p.requires_grad_(True)
         self.model.to(self.device)
         self.model.build_engine(share_from=self._share_engine)
+        if self.model.engine.train_precision == "fp32":
+            self._use_graph = False  # the fp32 parity mode runs eagerly (it rebuilds split weights with torch ops)
         self.optim = _FusedSGD(cfg.OPTIM)
         self.sched = build_lr_scheduler(self.optim, cfg.OPTIM)
         key = f"MultiModalPromptLearner_{self.client_id}"

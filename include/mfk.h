@@ -167,6 +167,18 @@ int mfk_attn_rows_bwd(const void* qkv, const int* rows, const void* d_out_rows, 
 int mfk_quickgelu_split_bf16x3(const float* u, void* out_bf16, int rows, int D, void* stream);
 int mfk_patch_im2col_f32(const float* img, float* out, int B, int S, void* stream);
 int mfk_attn_fwd_f32(const float* qkv, float* out, int N, int T, int heads, int causal, void* stream);
+/* fp32 TRAINING mode (cfg PREC = "fp32": the reference calls clip_model.float() and trains the fp32 model,
+ * trainers/maple.py:438-439, 590): the backward pieces between the split-operand GEMMs.
+ *  - mfk_attn_bwd_f32: dqkv fp32 [N*T, 3D] from d_out fp32 [N*T, D] and the forward's fp32 qkv (softmax recomputed;
+ *    stat_ws: 2*N*heads*T floats of scratch for log-sum-exp and delta); autograd of nn.MultiheadAttention's core
+ *    (clip/model.py:303-305), T <= 256;
+ *  - mfk_dquickgelu_mul_f32: du = dact * QuickGELU'(u) (clip/model.py:162-164);
+ *  - mfk_split_bf16x3_rhs: out[rows, 3D] = [hi | hi | lo], the B-side packing for activations (wgrad dY^T X of
+ *    resblocks.11 as ONE mfk_gemm_bf16_at_b over 3*rows: the [rows, 3D] buffers are read as [3 rows, D]).   */
+int mfk_attn_bwd_f32(const float* qkv, const float* d_out, float* dqkv, float* stat_ws, int N, int T, int heads,
+                     int causal, void* stream);
+int mfk_dquickgelu_mul_f32(const float* dact, const float* u, float* du, long long n, void* stream);
+int mfk_split_bf16x3_rhs(const float* x, void* out_bf16, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------ prompt-learner projections (fp32)
  * y[m,N] = x[m,K] W[N,K]^T + b (trainers/maple.py:194-215; m = n_ctx) and its backward.               */
