@@ -586,7 +586,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sP = sV + kvBytes;               // [2 groups][nkb][128 x 128 B]: P of the group's tile (also stages its O)
   if (threadIdx.x == 0 && (sP + 2 * (size_t)pBytes) - smem_raw_tc > (ptrdiff_t)p.smem_bytes) __trap();  // layout fits
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   constexpr int kCtl = FWD_GROUPS * TC_SOFTMAX_WARPS;  // control warp
   const int n_units = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -623,7 +623,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == kCtl + 2) {
     // ============================ loader: TMA loads of Q/K and V (one thread) ============================
-    if (lane == 0) {
+    if (elect_one()) {
       auto issue_qk = [&](int u) {
         int n, h;
         unit_coords(u, n, h);
@@ -653,7 +653,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp >= kCtl) {
     // ============================ MMA issuer of query tile mt (one thread per group) ============================
     const int mt = warp - kCtl;
-    if (lane == 0 && mt < NT) {
+    if (mt < NT && elect_one()) {  // (elect_one, not a lane test: UMMA descriptors stay in uniform registers)
       const uint32_t idesc_s = umma_idesc_bf16(128, Tk, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       const int ksteps = Tk / 16;
@@ -1210,7 +1210,11 @@ using namespace mfk;
 
 // 8 compute warps + two single-thread MMA issuers: tcgen05.mma issue costs ~70 cycles per instruction from one
 // thread, and a block needs 32 of them, so S/dP + dQ and dV + dK are issued from two warps in parallel.
-constexpr int FUSED_THREADS = (TC_SOFTMAX_WARPS + 2) * 32;
+// + 4 drain warps (one per TMEM lane quarter): dK_j / dV_j / dQ_i leave TMEM -> bf16 -> their own staging rows ->
+// coalesced global stores while the compute warps and the tensor core are already on the next key tile / the next
+// unit (the drains were 7.8 k of a unit's 23 k cycles when the compute warps did them between blocks).
+constexpr int FUSED_DRAIN_WARPS = 4;
+constexpr int FUSED_THREADS = (TC_SOFTMAX_WARPS + 2 + FUSED_DRAIN_WARPS) * 32;
 
 struct AttnBwdFusedParams {
   const float* lse;
@@ -1229,6 +1233,7 @@ struct AttnBwdFusedParams {
 
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmDo,
+                         const __grid_constant__ CUtensorMap tmQkv2, const __grid_constant__ CUtensorMap tmDo2,
                          const AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw_f[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_f) + 1023) & ~uintptr_t(1023));
@@ -1240,18 +1245,25 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   uint8_t* sdO = sV + fullBytes;
   uint8_t* sP = sdO + fullBytes;   // [2 column blocks][128 rows x 128 B]
   uint8_t* sdS = sP + 32768;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
-  uint64_t* ld_full = bars;
+  uint8_t* sEpi = sdS + 32768;     // [4 drain warps][32 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 16384);
+  uint64_t* ld_full = bars;        // first 128 rows of Q, K, V, dO (two arrivals: K + V, Q + dO)
+  uint64_t* ld2_full = bars + 9;   // rows [128, T) of the four operands (T > 128)
   uint64_t* sd_full = bars + 1;
   uint64_t* ds_full = bars + 2;
   uint64_t* mma2_done = bars + 3;
   uint64_t* dkv_free = bars + 4;
   uint64_t* unit_free = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* s_lse = reinterpret_cast<float*>(bars + 8);   // [256] log-sum-exp of the unit's query rows
-  float* s_delta = s_lse + 256;                        // [256] delta = rowsum(dO * O)
+  uint64_t* acc_done = bars + 6;   // every MMA into dK_j / dV_j (and, on the last key tile, dQ) has retired
+  uint64_t* sdp_issued = bars + 7;  // issuer A has queued S / dP of the next block: issuer B's dV / dK may follow
+  uint64_t* stats_full = bars + 10;  // [2] lse / delta of a unit's query rows are in smem (one arrival per drain warp);
+                                     //     barrier u & 1 for unit u, so that the statistics may run a whole unit ahead
+  uint64_t* sdp_consumed = bars + 12;  // every compute warp has read S / dP of the block out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_lse = reinterpret_cast<float*>(bars + 14);   // [2][256] log-sum-exp of the unit's query rows (unit parity)
+  float* s_delta = s_lse + 512;                         // [2][256] delta = rowsum(dO * O)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int n_units = (p.total_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nblk = NT * NT;
 
@@ -1259,17 +1271,35 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     if (lane == 0) {
       tma_prefetch_desc(&tmQkv);
       tma_prefetch_desc(&tmDo);
-      mbar_init(ld_full, 1);
+      mbar_init(ld_full, 2);
+      mbar_init(ld2_full, 1);
       mbar_init(sd_full, 1);
       mbar_init(ds_full, TC_SOFTMAX_WARPS);
       mbar_init(mma2_done, 2);  // one commit per issuing thread
-      mbar_init(dkv_free, TC_SOFTMAX_WARPS);
-      mbar_init(unit_free, TC_SOFTMAX_WARPS);
+      mbar_init(acc_done, 2);
+      mbar_init(sdp_issued, 1);
+      mbar_init(&stats_full[0], FUSED_DRAIN_WARPS);
+      mbar_init(&stats_full[1], FUSED_DRAIN_WARPS);
+      mbar_init(sdp_consumed, TC_SOFTMAX_WARPS);
+      mbar_init(dkv_free, FUSED_DRAIN_WARPS);
+      mbar_init(unit_free, FUSED_DRAIN_WARPS);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  // The second tile of each operand is loaded as a box of R2 = 16 * ceil((T - 128) / 16) rows only (80 of 128 at
+  // T = 199): rows [R2, 128) of it are never written by TMA and are zeroed once here — they feed MMAs as M / N rows whose
+  // results are masked, so they must be finite.
+  const int R2 = NT == 2 ? (p.T - 128 + 15) / 16 * 16 : 0;
+  if (NT == 2 && R2 < 128) {
+    const int per = (128 - R2) * 8;  // 16-byte chunks per buffer
+    for (int idx = (int)threadIdx.x; idx < 4 * per; idx += (int)blockDim.x) {
+      uint8_t* base = (idx / per == 0 ? sQ : idx / per == 1 ? sK : idx / per == 2 ? sV : sdO) + 16384 + R2 * 128;
+      reinterpret_cast<uint4*>(base)[idx % per] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -1279,8 +1309,138 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
   pdl_trigger();
   pdl_wait();
 
-  if (warp >= TC_SOFTMAX_WARPS) {
-    if (lane == 0) {
+  if (warp >= TC_SOFTMAX_WARPS + 2) {
+    // ============================ drain warps: accumulators -> global ============================
+    // A thread owns one TMEM lane (= row) of its warp's lane quarter; 32 lanes storing 128 bytes of 32 different
+    // rows each would cost 32 memory wavefronts per instruction, so the bf16 rows are staged in the warp's own 4 KB
+    // (16-byte chunks XOR-swizzled by row) and leave as 4 whole 128-byte rows per instruction. Warp-local: no barrier
+    // with the other drain warps.
+    const int q = warp & 3;
+    const uint32_t x7 = (uint32_t)lane & 7u;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t my = smem_u32(sEpi) + (uint32_t)q * 4096u;
+    uint32_t kt_ctr = 0;
+    int trc_n = 0;
+    (void)trc_n;
+    // lse and delta = rowsum(dO * O) of the unit's query rows -> smem. Coalesced: a call covers 32 of the (<= 256)
+    // rows; 8 lanes read the 128 bytes of one (row, head) of O and of dO, 4 rows per instruction, and the row dot
+    // product is finished with 3 shuffles (one lane per row reading its own 128 bytes would cost 32 memory
+    // wavefronts per instruction instead of 4).
+    auto row_stats_32 = [&](int u, int r0) {
+      const int w = (int)blockIdx.x + u * (int)gridDim.x;
+      const int h = w % p.heads, n = w / p.heads;
+      const size_t sidx = ((size_t)n * p.heads + h) * p.T;
+      float* s_lse_u = s_lse + (u & 1) * 256;
+      float* s_delta_u = s_delta + (u & 1) * 256;
+      {
+        const int qrow = r0 + lane;
+        s_lse_u[qrow] = qrow < p.T ? p.lse[sidx + qrow] : 0.f;
+      }
+      // all 16 loads are issued before the first use (one memory round trip instead of eight)
+      uint4 va[8], vb[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int qrow = min(r0 + g * 4 + (lane >> 3), p.T - 1);  // clamped: rows >= T are discarded below
+        const size_t off = ((size_t)n * p.T + qrow) * D + h * HD + (lane & 7) * 8;
+        va[g] = __ldg(reinterpret_cast<const uint4*>(p.out + off));
+        vb[g] = __ldg(reinterpret_cast<const uint4*>(p.d_out + off));
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int qrow = r0 + g * 4 + (lane >> 3);
+        const uint4 a = va[g], b = vb[g];
+        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+        const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+        float dsum = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
+                     (a3.x * b3.x + a3.y * b3.y);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+        if ((lane & 7) == 0) s_delta_u[qrow] = qrow < p.T ? dsum : 0.f;
+      }
+    };
+    // Statistics of unit u -> buffer and barrier u & 1, 64 rows per drain warp. Unit 0 up front, unit u + 1 at the start of
+    // this warp's pass over unit u: the drains of unit u - 1 are behind it, so the compute warps are past their wait on
+    // barrier (u + 1) & 1 for unit u - 1 (a barrier must never run two phases ahead of a waiter) and have read that
+    // buffer; the statistics are then ready a whole unit before they are needed.
+    auto row_stats = [&](int u) {
+      if (u >= n_units) return;
+      for (int r0 = q * 64; r0 < q * 64 + 64; r0 += 32)
+        if (r0 < R) row_stats_32(u, r0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stats_full[u & 1]);
+    };
+    row_stats(0);
+    for (int u = 0; u < n_units; ++u) {
+      const int w = (int)blockIdx.x + u * (int)gridDim.x;
+      const int h = w % p.heads, n = w / p.heads;
+      row_stats(u + 1);
+      // rows of the tile start at sequence position seq0; column offset 0 q | D k | 2D v
+      auto drain = [&](uint32_t col, float sc, int seq0, int coff, uint64_t* release) {
+        const int r0 = seq0 + q * 32;
+        if (r0 < p.T) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tmem_ld32(tlane + col + (uint32_t)(hh * 32), r);
+            tc_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + (uint32_t)lane * 128u +
+                                                                        ((((uint32_t)hh * 4 + t) ^ x7) << 4)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t]) * sc, __uint_as_float(r[8 * t + 1]) * sc)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t + 2]) * sc, __uint_as_float(r[8 * t + 3]) * sc)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t + 4]) * sc, __uint_as_float(r[8 * t + 5]) * sc)),
+                           "r"(pack_bf16(__uint_as_float(r[8 * t + 6]) * sc, __uint_as_float(r[8 * t + 7]) * sc))
+                           : "memory");
+          }
+        }
+        if (release) {  // the accumulator has been read: the MMAs that overwrite it may go while the rows are stored
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(release);
+        } else {
+          __syncwarp();
+        }
+        if (r0 < p.T) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int idx = lane + m * 32;
+            const int row = idx >> 3, ch = idx & 7;
+            if (r0 + row < p.T) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(my + (uint32_t)row * 128u + (((uint32_t)ch ^ ((uint32_t)row & 7u)) << 4)));
+              *reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.T + r0 + row) * (3 * (size_t)D) + coff + h * HD +
+                                        ch * 8) = v;
+            }
+          }
+          __syncwarp();  // the staging rows are rewritten by this warp's next tile
+        }
+      };
+      for (int j = 0; j < NT; ++j) {
+#ifdef MFK_TRACE2
+        if (q == 0 && lane == 0) TRC(3);
+#endif
+        mbar_wait(acc_done, kt_ctr & 1u);
+#ifdef MFK_TRACE2
+        if (q == 0 && lane == 0) TRC(3);
+#endif
+        ++kt_ctr;
+        tc_fence_after();
+        drain(colDK, p.scale, j * 128, D, nullptr);
+        drain(colDV, 1.f, j * 128, 2 * D, dkv_free);
+        if (j == NT - 1)
+          for (int ii = 0; ii < NT; ++ii)
+            drain(colDQ + (uint32_t)ii * 64u, p.scale, ii * 128, 0, ii == NT - 1 ? unit_free : nullptr);
+#ifdef MFK_TRACE2
+        if (q == 0 && lane == 0) TRC(3);
+#endif
+      }
+    }
+  } else if (warp >= TC_SOFTMAX_WARPS) {
+    if (elect_one()) {
       const bool issuer_a = warp == TC_SOFTMAX_WARPS;  // A: TMA loads, S / dP, dQ.   B: dV, dK.
       uint32_t blk_ctr = 0, kt_ctr = 0;
       const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0, 0);
@@ -1309,55 +1469,124 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
       // time even with the predicate always true).
       const int ks_last = (p.T - (NT - 1) * 128 + 15) / 16;
       int trc_n = 0;
-      auto issue_loads = [&](int u) {
+      // Operand loads of unit u, in three groups that follow the order in which the previous unit releases the
+      // buffers (T > 128: blocks run (i0,j0) (i1,j0) (i0,j1) (i1,j1)): K_0 / V_0 are last read by block 1, Q_0 / dO_0
+      // by block 2, the second tiles by block 3 — so only the (short) second tiles are fetched after the unit's last
+      // MMA, and they are not needed before block 1 of the next unit.
+      auto issue_kv0 = [&](int u) {
         const int w = (int)blockIdx.x + u * (int)gridDim.x;
-        const int h = w % p.heads, n = w / p.heads;
-        mbar_arrive_expect_tx(ld_full, 4u * fullBytes);
-        const int row0 = n * p.T;
-        tma_load_2d(&tmQkv, ld_full, sQ, h * HD, row0);
+        const int h = w % p.heads, row0 = (w / p.heads) * p.T;
+        mbar_arrive_expect_tx(ld_full, 32768u);
         tma_load_2d(&tmQkv, ld_full, sK, D + h * HD, row0);
         tma_load_2d(&tmQkv, ld_full, sV, 2 * D + h * HD, row0);
+      };
+      auto issue_qdo0 = [&](int u) {
+        const int w = (int)blockIdx.x + u * (int)gridDim.x;
+        const int h = w % p.heads, row0 = (w / p.heads) * p.T;
+        mbar_arrive_expect_tx(ld_full, 32768u);
+        tma_load_2d(&tmQkv, ld_full, sQ, h * HD, row0);
         tma_load_2d(&tmDo, ld_full, sdO, h * HD, row0);
       };
+      auto issue_second = [&](int u) {
+        if (NT < 2) return;
+        const int w = (int)blockIdx.x + u * (int)gridDim.x;
+        const int h = w % p.heads, row1 = (w / p.heads) * p.T + 128;
+        mbar_arrive_expect_tx(ld2_full, 4u * (uint32_t)R2 * 128u);
+        tma_load_2d(&tmQkv2, ld2_full, sQ + 16384, h * HD, row1);
+        tma_load_2d(&tmDo2, ld2_full, sdO + 16384, h * HD, row1);
+        tma_load_2d(&tmQkv2, ld2_full, sK + 16384, D + h * HD, row1);
+        tma_load_2d(&tmQkv2, ld2_full, sV + 16384, 2 * D + h * HD, row1);
+      };
       if (issuer_a) {
-        if (n_units > 0) issue_loads(0);
+        if (n_units > 0) {
+          issue_kv0(0);
+          issue_qdo0(0);
+          issue_second(0);
+        }
         for (int u = 0; u < n_units; ++u) {
-          // the TMEM accumulators of the previous unit must be drained; its loads were issued early (below)
-          mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
-          TRC(0);  // unit start (previous unit drained)
-          mbar_wait(ld_full, (uint32_t)u & 1u);
+          // this unit's loads were issued early (below); S / dP of its first block only need the S / dP columns, which
+          // the compute warps have left (ds_full of the previous unit's last block) — the accumulators of the previous
+          // unit may still be draining and are waited for before the first dQ MMA
+          TRC(0);  // unit start
+          if (u == 0 || NT != 2) {  // (T > 128: issued inside the previous unit's last block, below)
+            mbar_wait(ld_full, (uint32_t)u & 1u);
+            tc_fence_after();
+            issue_sdp(0, 0);
+          }
           TRC(0);  // loads landed
-          tc_fence_after();
-          issue_sdp(0, 0);
           TRC(0);  // S/dP issued
           for (int k = 0; k < nblk; ++k, ++blk_ctr) {
             const int j = k / NT, i = k % NT;
+            // S / dP of the NEXT block go out as soon as the compute warps have read this block's S / dP out of TMEM
+            // (about half-way through their pass): they are complete when the warps come back for them, and their exp /
+            // dS arithmetic then overlaps the second-stage MMAs of this block. After the unit's last block the next
+            // block is the first one of the next unit (T > 128: its first operand tiles were requested during blocks 1
+            // and 2, below).
+            mbar_wait(sdp_consumed, blk_ctr & 1u);
+            tc_fence_after();
+            if (k + 1 < nblk) {
+              if (k == 0) {  // block 1 is the first to touch the second tiles
+                mbar_wait(ld2_full, (uint32_t)u & 1u);
+                tc_fence_after();
+              }
+              issue_sdp((k + 1) % NT, (k + 1) / NT);
+            } else if (NT == 2 && u + 1 < n_units) {
+              mbar_wait(ld_full, (uint32_t)(u + 1) & 1u);
+              tc_fence_after();
+              issue_sdp(0, 0);
+            }
+            // the compute warps wait for exactly these MMAs next: issuer B holds its 16 second-stage MMAs of block k
+            // back until they are queued
+            mbar_arrive(sdp_issued);
             mbar_wait(ds_full, blk_ctr & 1u);
             TRC(0);  // staged operands ready
-            // S/dP of the NEXT block go first: the compute warps have finished reading the S/dP columns, and their
-            // exp / dS arithmetic for block k + 1 then overlaps the second-stage MMAs of block k (they wait for
-            // mma2_done before overwriting the staged P / dS tiles those MMAs read).
             tc_fence_after();
-            if (k + 1 < nblk) issue_sdp((k + 1) % NT, (k + 1) / NT);
             const uint64_t bk = dKm + 1024ull * j;
             const uint32_t acc_j = j > 0;
             const int ks_j = j == NT - 1 ? ks_last : 8;
+            if (k == 0) {  // dQ of the previous unit drained
+              mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
+              tc_fence_after();
+            }
+#ifndef MFK_EXP_NO_DQ
             for (int ks = 0; ks < ks_j; ++ks)  // dQ_i += dS K_j        (K = keys of tile j: 2 column blocks x 4 k-steps)
+#else
+            for (int ks = 0; ks < 0; ++ks)
+#endif
               umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, dDsk + 1024ull * (ks >> 2) + 2ull * (ks & 3),
                         bk + 128ull * ks, idesc_kt, acc_j | (ks > 0));
             umma_commit(mma2_done);
+            if (i == NT - 1) umma_commit(acc_done);
             TRC(0);  // second-stage (+ next S/dP) issued
+            // T > 128, blocks (i0,j0) (i1,j0) (i0,j1) (i1,j1): K_0 / V_0 are last read by block 1, Q_0 / dO_0 by block 2.
+            // Their refill with the next unit's rows starts as soon as those MMAs have retired (this thread has nothing
+            // else to do until the compute warps are half-way through the next block).
+            if (NT == 2 && u + 1 < n_units && (k == 1 || k == 2)) {
+              mbar_wait(mma2_done, blk_ctr & 1u);
+              if (k == 1) issue_kv0(u + 1);
+              else issue_qdo0(u + 1);
+            }
           }
-          // Q, K, V, dO are free once the last block's MMAs (of both issuers) have retired: the next unit's loads run
-          // under this unit's epilogue (the compute warps read TMEM and lse / O / dO from global memory)
+          // the second tiles (T > 128) resp. all operands are free once the last block's MMAs of both issuers have retired
           mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
-          if (u + 1 < n_units) issue_loads(u + 1);
+          if (u + 1 < n_units) {
+            if (NT == 2) {
+              issue_second(u + 1);
+            } else {
+              issue_kv0(u + 1);
+              issue_qdo0(u + 1);
+            }
+          }
         }
       } else {
         for (int u = 0; u < n_units; ++u) {
           for (int k = 0; k < nblk; ++k, ++blk_ctr) {
             const int j = k / NT, i = k % NT;
             mbar_wait(ds_full, blk_ctr & 1u);
+            mbar_wait(sdp_issued, blk_ctr & 1u);
+#ifdef MFK_TRACE2
+            TRC(2);
+#endif
             if (i == 0 && j > 0) {  // accumulators of the previous key tile must have been drained
               mbar_wait(dkv_free, kt_ctr & 1u);
               ++kt_ctr;
@@ -1366,11 +1595,23 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
             const uint64_t bdo = dDom + 1024ull * i, bq = dQm + 1024ull * i;
             const uint32_t acc_i = i > 0;
             const int ks_i = i == NT - 1 ? ks_last : 8;
+#ifndef MFK_EXP_NO_DV
             for (int ks = 0; ks < ks_i; ++ks)  // dV_j += P^T dO_i   (K = query rows of tile i, 16 per MMA)
+#else
+            for (int ks = 0; ks < 0; ++ks)
+#endif
               umma_bf16(tmem_base + colDV, dPm + 128ull * ks, bdo + 128ull * ks, idesc_tt, acc_i | (ks > 0));
+#ifndef MFK_EXP_NO_DK
             for (int ks = 0; ks < ks_i; ++ks)  // dK_j += dS^T Q_i
+#else
+            for (int ks = 0; ks < 0; ++ks)
+#endif
               umma_bf16(tmem_base + colDK, dDsm + 128ull * ks, bq + 128ull * ks, idesc_tt, acc_i | (ks > 0));
             umma_commit(mma2_done);
+            if (i == NT - 1) umma_commit(acc_done);
+#ifdef MFK_TRACE2
+            TRC(2);
+#endif
           }
           // the last key tile's dkv_free arrive is consumed here so the phase counters stay in step
           mbar_wait(dkv_free, kt_ctr & 1u);
@@ -1388,93 +1629,94 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     uint32_t blk_ctr = 0;
     int trc_n = 0;
     const bool trc_me = warp == 0 && lane == 0;
-    // lse and delta = rowsum(dO * O) of the unit's query rows -> smem. Coalesced: this warp owns 32 of the (<= 256)
-    // rows; 8 lanes read the 128 bytes of one (row, head) of O and of dO, 4 rows per instruction, and the row dot
-    // product is finished with 3 shuffles (one lane per row reading its own 128 bytes would cost 32 memory
-    // wavefronts per instruction instead of 4).
-    auto row_stats = [&](int u) {
-      const int w = (int)blockIdx.x + u * (int)gridDim.x;
-      const int h = w % p.heads, n = w / p.heads;
-      const size_t sidx = ((size_t)n * p.heads + h) * p.T;
-      const int r0 = warp * 32;
-      {
-        const int qrow = r0 + lane;
-        s_lse[qrow] = qrow < p.T ? p.lse[sidx + qrow] : 0.f;
-      }
-      // all 16 loads are issued before the first use (one memory round trip instead of eight)
-      uint4 va[8], vb[8];
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int qrow = min(r0 + g * 4 + (lane >> 3), p.T - 1);  // clamped: rows >= T are discarded below
-        const size_t off = ((size_t)n * p.T + qrow) * D + h * HD + (lane & 7) * 8;
-        va[g] = __ldg(reinterpret_cast<const uint4*>(p.out + off));
-        vb[g] = __ldg(reinterpret_cast<const uint4*>(p.d_out + off));
-      }
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int qrow = r0 + g * 4 + (lane >> 3);
-        const uint4 a = va[g], b = vb[g];
-        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-        const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
-        float dsum = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y) +
-                     (a3.x * b3.x + a3.y * b3.y);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-        dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
-        if ((lane & 7) == 0) s_delta[qrow] = qrow < p.T ? dsum : 0.f;
-      }
-    };
-    // The first unit's are fetched up front (under its TMA loads); those of unit u + 1 inside unit u's last block,
-    // where this warp would otherwise idle waiting for the second-stage MMAs.
-    if (n_units > 0) row_stats(0);
+#ifdef MFK_TRACE2
+    int trc4 = 0;
+#endif
     for (int u = 0; u < n_units; ++u) {
       const int w = (int)blockIdx.x + u * (int)gridDim.x;
       const int h = w % p.heads, n = w / p.heads;
-      asm volatile("bar.sync 2, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");  // row stats of this unit are in smem
-      const float Lc[2] = {s_lse[rl], s_lse[128 + rl]}, dcache[2] = {s_delta[rl], s_delta[128 + rl]};
+      mbar_wait(&stats_full[u & 1], ((uint32_t)u >> 1) & 1u);  // row statistics of this unit are in smem (drain warps)
+#ifdef MFK_TRACE2
+      if (p.trace && trc_me && trc4 < 60) p.trace[4 * 64 + trc4++] = clock64();
+#endif
+      const float* u_lse = s_lse + (u & 1) * 256;
+      const float* u_delta = s_delta + (u & 1) * 256;
+      const float Lc[2] = {u_lse[rl], u_lse[128 + rl]}, dcache[2] = {u_delta[rl], u_delta[128 + rl]};
       for (int k = 0; k < nblk; ++k, ++blk_ctr) {
         const int j = k / NT, i = k % NT;
         const int qrow = i * 128 + rl;
         const bool qok = qrow < p.T;
-        const float L = i == 0 ? Lc[0] : Lc[1];
+        const float L = qok ? (i == 0 ? Lc[0] : Lc[1]) : INFINITY;  // dead rows: exp2(-inf) = 0
         const float Dl = i == 0 ? dcache[0] : dcache[1];
         if (trc_me) TRC(1);  // about to wait for S/dP
         mbar_wait(sd_full, blk_ctr & 1u);
         if (trc_me) TRC(1);  // S/dP ready
         tc_fence_after();
+        // A warp whose 32 query rows all lie beyond T (T = 199: the last quarter of the second query tile) has nothing to
+        // stage: those rows of P / dS are only ever read as the K tail that the second-stage MMAs skip (ks_last) or as
+        // M rows whose results are discarded.
+        const bool rows_live = i * 128 + q * 32 < p.T;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c = half * 32 + cc * 64;
-          uint32_t rs[32], rd[32];
-          tmem_ld32(tlane + colS + (uint32_t)c, rs);
-          tmem_ld32(tlane + colDP + (uint32_t)c, rd);
-          tc_wait_ld();
-          float pv[32], dv[32];
           const int key0 = j * 128 + c;
-          const bool full = key0 + 32 <= p.T;
+          // columns beyond T likewise (T = 199: keys 224.. of the second key tile): never read as K, discarded as M
+          const bool live = rows_live && key0 < p.T;
+          uint32_t pk[16], dk[16];
+          if (live) {
+            uint32_t rs[32], rd[32];
+            tmem_ld32(tlane + colS + (uint32_t)c, rs);
+            tmem_ld32(tlane + colDP + (uint32_t)c, rd);
+            tc_wait_ld();
+            if (cc == 1) {  // this warp is done with the block's S / dP columns
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(sdp_consumed);
+            }
+            if (key0 + 32 <= p.T) {
+              // no masks: L = +inf for query rows beyond T makes their exponentials (and with them dS) exactly 0
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const float e = fast_exp2(__uint_as_float(rs[jj]) * p.c1 - L);
-            const float pr = (qok && (full || key0 + jj < p.T)) ? e : 0.f;
-            pv[jj] = pr;
-            dv[jj] = pr * (__uint_as_float(rd[jj]) - Dl);
+              for (int jj = 0; jj < 16; ++jj) {
+                const float e0 = fast_exp2(__uint_as_float(rs[2 * jj]) * p.c1 - L);
+                const float e1 = fast_exp2(__uint_as_float(rs[2 * jj + 1]) * p.c1 - L);
+                pk[jj] = pack_bf16(e0, e1);
+                dk[jj] = pack_bf16(e0 * (__uint_as_float(rd[2 * jj]) - Dl), e1 * (__uint_as_float(rd[2 * jj + 1]) - Dl));
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                const float e0 = key0 + 2 * jj < p.T ? fast_exp2(__uint_as_float(rs[2 * jj]) * p.c1 - L) : 0.f;
+                const float e1 = key0 + 2 * jj + 1 < p.T ? fast_exp2(__uint_as_float(rs[2 * jj + 1]) * p.c1 - L) : 0.f;
+                pk[jj] = pack_bf16(e0, e1);
+                dk[jj] = pack_bf16(e0 * (__uint_as_float(rd[2 * jj]) - Dl), e1 * (__uint_as_float(rd[2 * jj + 1]) - Dl));
+              }
+            }
+          }
+          if (cc == 1 && !live) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_consumed);
           }
           const uint32_t boff = (uint32_t)(c >> 6) * 16384u;
           const uint32_t ch0 = (uint32_t)(c & 63) >> 3;
           // the staged P / dS tiles are still being read by the previous block's second-stage MMAs (which now run
           // concurrently with the arithmetic above): wait for them before the first store of this block
-          if (cc == 0 && blk_ctr > 0) mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
+          if (cc == 0 && blk_ctr > 0) {
+            if (trc_me) TRC(1);  // first half of the arithmetic done
+            mbar_wait(mma2_done, (blk_ctr - 1u) & 1u);
+            if (trc_me) TRC(1);  // staged tiles of the previous block released
+          }
+          if (live) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t off = boff + (((ch0 + t) ^ x7) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + off),
-                         "r"(pack_bf16(pv[8 * t], pv[8 * t + 1])), "r"(pack_bf16(pv[8 * t + 2], pv[8 * t + 3])),
-                         "r"(pack_bf16(pv[8 * t + 4], pv[8 * t + 5])), "r"(pack_bf16(pv[8 * t + 6], pv[8 * t + 7]))
-                         : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dsrow + off),
-                         "r"(pack_bf16(dv[8 * t], dv[8 * t + 1])), "r"(pack_bf16(dv[8 * t + 2], dv[8 * t + 3])),
-                         "r"(pack_bf16(dv[8 * t + 4], dv[8 * t + 5])), "r"(pack_bf16(dv[8 * t + 6], dv[8 * t + 7]))
-                         : "memory");
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t off = boff + (((ch0 + t) ^ x7) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + off), "r"(pk[4 * t]), "r"(pk[4 * t + 1]),
+                           "r"(pk[4 * t + 2]), "r"(pk[4 * t + 3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dsrow + off), "r"(dk[4 * t]), "r"(dk[4 * t + 1]),
+                           "r"(dk[4 * t + 2]), "r"(dk[4 * t + 3])
+                           : "memory");
+            }
           }
         }
         tc_fence_before();
@@ -1482,65 +1724,9 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
         if (trc_me) TRC(1);  // staged
-        if (k == nblk - 1 && u + 1 < n_units) row_stats(u + 1);  // (every thread read this unit's at its start)
-        if (i == NT - 1) {
-          // ---- key tile j complete: dK_j (scaled), dV_j -> global
-          mbar_wait(mma2_done, blk_ctr & 1u);
-          if (trc_me) TRC(1);  // second-stage done
-          tc_fence_after();
-          // Accumulators -> bf16 tiles staged in the (now idle) P / dS buffers -> coalesced global stores: a thread
-          // owns one TMEM lane (= row), and 32 lanes storing 64 bytes of 32 different rows each cost 32 memory
-          // wavefronts per instruction; from the staged tile a warp instruction writes 4 whole 128-byte rows.
-          // Tiles: 0 dK_j, 1 dV_j (sP), 2.. dQ_i (sdS, last key tile only). 16-byte chunks XOR-swizzled by row.
-          const int ntile = (j == NT - 1) ? 2 + NT : 2;
-          auto stage_tile = [&](int tile, uint32_t col, float sc) {
-            uint32_t r[32];
-            tmem_ld32(tlane + col + (uint32_t)(half * 32), r);
-            tc_wait_ld();
-            const uint32_t base = smem_u32(sP) + (uint32_t)tile * 16384u + (uint32_t)rl * 128u;
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((((uint32_t)half * 4 + t) ^ x7) << 4)),
-                           "r"(pack_bf16(__uint_as_float(r[8 * t]) * sc, __uint_as_float(r[8 * t + 1]) * sc)),
-                           "r"(pack_bf16(__uint_as_float(r[8 * t + 2]) * sc, __uint_as_float(r[8 * t + 3]) * sc)),
-                           "r"(pack_bf16(__uint_as_float(r[8 * t + 4]) * sc, __uint_as_float(r[8 * t + 5]) * sc)),
-                           "r"(pack_bf16(__uint_as_float(r[8 * t + 6]) * sc, __uint_as_float(r[8 * t + 7]) * sc))
-                           : "memory");
-          };
-          stage_tile(0, colDK, p.scale);
-          stage_tile(1, colDV, 1.f);
-          if (j == NT - 1)
-            for (int ii = 0; ii < NT; ++ii) stage_tile(2 + ii, colDQ + (uint32_t)ii * 64u, p.scale);
-          asm volatile("bar.sync 3, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
-          for (int tile = 0; tile < ntile; ++tile) {
-            // tile rows are keys of tile j (dK, dV) or queries of tile (tile - 2); column offset 0 q | D k | 2D v
-            const int seq0 = tile < 2 ? j * 128 : (tile - 2) * 128;
-            const int coff = tile == 0 ? D : tile == 1 ? 2 * D : 0;
-            const uint32_t tbase = smem_u32(sP) + (uint32_t)tile * 16384u;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int idx = (int)threadIdx.x + m * (TC_SOFTMAX_WARPS * 32);
-              const int row = idx >> 3, ch = idx & 7;
-              if (seq0 + row < p.T) {
-                uint4 v;
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                             : "r"(tbase + (uint32_t)row * 128u + (((uint32_t)ch ^ ((uint32_t)row & 7u)) << 4)));
-                *reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.T + seq0 + row) * (3 * (size_t)D) + coff + h * HD +
-                                          ch * 8) = v;
-              }
-            }
-          }
-          // the staged tiles are overwritten by the next block's P / dS: every thread must have read them
-          asm volatile("bar.sync 3, %0;" ::"n"(TC_SOFTMAX_WARPS * 32) : "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (trc_me) TRC(1);  // epilogue stores issued
-          if (lane == 0) {
-            mbar_arrive(dkv_free);
-            if (j == NT - 1) mbar_arrive(unit_free);
-          }
-        }
+#ifdef MFK_TRACE2
+        if (p.trace && k == nblk - 1 && trc_me && trc4 < 60) p.trace[4 * 64 + trc4++] = clock64();
+#endif
       }
     }
   }
@@ -1581,15 +1767,22 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   p.total_units = N * heads;
   p.c1 = 0.125f * kLog2e; p.scale = 0.125f;
   p.trace = g_attn_trace;
-  CUtensorMap tmQkv, tmDo;
+  // boxes: 128 rows for the first tile of an operand, 16 * ceil((T - 128) / 16) rows for the second
+  CUtensorMap tmQkv, tmDo, tmQkv2, tmDo2;
   int rc;
-  if ((rc = mfk_make_tmap_2d(&tmQkv, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;
-  if ((rc = mfk_make_tmap_2d(&tmDo, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, (uint32_t)p.R, 64, 128)) != MFK_OK) return rc;
-  const size_t smem = 4 * (size_t)p.R * 128 + 65536 + 128 + 2048 + 1024;
+  if ((rc = mfk_make_tmap_2d(&tmQkv, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, 128, 64, 128)) != MFK_OK) return rc;
+  if ((rc = mfk_make_tmap_2d(&tmDo, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, 128, 64, 128)) != MFK_OK) return rc;
+  tmQkv2 = tmQkv; tmDo2 = tmDo;
+  if (p.tiles == 2) {
+    const uint32_t r2 = (uint32_t)((T - 128 + 15) / 16 * 16);
+    if ((rc = mfk_make_tmap_2d(&tmQkv2, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, r2, 64, 128)) != MFK_OK) return rc;
+    if ((rc = mfk_make_tmap_2d(&tmDo2, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, r2, 64, 128)) != MFK_OK) return rc;
+  }
+  const size_t smem = 4 * (size_t)p.R * 128 + 65536 + 16384 + 128 + 4096 + 1024;
   e = cudaFuncSetAttribute(attn_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.total_units < g_attn_sms ? p.total_units : g_attn_sms;
-  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(FUSED_THREADS), smem, st, tmQkv, tmDo, p);
+  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(FUSED_THREADS), smem, st, tmQkv, tmDo, tmQkv2, tmDo2, p);
   if (e != cudaSuccess) return (int)e;
   return MFK_OK;
 }

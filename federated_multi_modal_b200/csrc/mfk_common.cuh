@@ -218,6 +218,22 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One deterministic leader of the (converged) warp. `if (elect_one()) { ... tcgen05.mma ... }` instead of
+// `if (lane == 0)`: ptxas then knows that exactly one thread runs the block and keeps the UMMA descriptors in uniform
+// registers; under a lane test it wraps every tcgen05.mma in an elect / R2UR x4 / R2UR.BROADCAST / branch loop
+// (~100 cycles per MMA from the issuing thread).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate, issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -429,7 +429,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
   // pair mode: the two CTAs of a cluster work on vertically adjacent M tiles of the same N range
@@ -484,7 +484,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int trc = 2;
@@ -549,7 +549,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0 && !(kPair && crank != 0)) {
+    if (!(kPair && crank != 0) && elect_one()) {  // (elect_one: no per-MMA elect / branch loop around tcgen05.mma)
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_mine; ++it) {

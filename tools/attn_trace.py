@@ -27,4 +27,12 @@ for i, v in enumerate(row[:33]):
     print(f"  {names_ctl[i % 11]:32s} {v:8d}" + ("   <-- next unit" if i % 11 == 0 and i else ""))
 print("compute warp 0:")
 row = [int(x) - base for x in t[1] if int(x) > 0]
-print("  ", row[:40])
+# per block: about to wait for S/dP, S/dP ready, [first half of the arithmetic done, previous block's staged tiles released]
+# (not in the very first block), staged
+print("  ", row[:60])
+names = ["wait", "ready", "math0", "released", "staged"]
+r = row[3:]  # first block of the launch has no mma2 wait
+for b in range(len(r) // 5):
+    x = r[b * 5:(b + 1) * 5]
+    print(f"  block {b + 1}: S/dP wait {x[1] - x[0]:5d}  math(1st half) {x[2] - x[1]:5d}  mma2 wait {x[3] - x[2]:5d}  "
+          f"stores + 2nd half {x[4] - x[3]:5d}" + (f"  -> next wait {r[(b + 1) * 5] - x[4]:5d}" if (b + 1) * 5 < len(r) else ""))
