@@ -868,7 +868,10 @@ extern "C" int mfk_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, in
   // 128 (barriers) + 2048 (exchange slots) rounded up to the tiles' 1024-byte alignment, then Q, K, V, 2 x P
   const size_t smem = 3072 + (size_t)p.m_tiles * 16384 + 2 * (size_t)p.Tk * 128 + 2 * (size_t)nkb * 16384;
   p.smem_bytes = (unsigned)smem;
-  const int grid = p.total_items < g_attn_sms ? p.total_items : g_attn_sms;
+  // every CTA runs the same number of units (384 units on 148 SMs = 3 rounds either way): the balanced grid (128) leaves
+  // the other SMs to the concurrent text-tower stream instead of parking CTAs that finish a round early
+  const int rounds = (p.total_items + g_attn_sms - 1) / g_attn_sms;
+  const int grid = (p.total_items + rounds - 1) / rounds;
   cudaError_t e;
   if (causal) {
     e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1234,7 +1237,7 @@ struct AttnBwdFusedParams {
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmDo,
                          const __grid_constant__ CUtensorMap tmQkv2, const __grid_constant__ CUtensorMap tmDo2,
-                         const AttnBwdFusedParams p) {
+                         const __grid_constant__ CUtensorMap tmOut, const AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw_f[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_f) + 1023) & ~uintptr_t(1023));
   const int D = p.heads * HD, R = p.R, NT = p.tiles;
@@ -1271,6 +1274,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     if (lane == 0) {
       tma_prefetch_desc(&tmQkv);
       tma_prefetch_desc(&tmDo);
+      tma_prefetch_desc(&tmOut);
       mbar_init(ld_full, 2);
       mbar_init(ld2_full, 1);
       mbar_init(sd_full, 1);
@@ -1359,26 +1363,36 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         if ((lane & 7) == 0) s_delta_u[qrow] = qrow < p.T ? dsum : 0.f;
       }
     };
-    // Statistics of unit u -> buffer and barrier u & 1, 64 rows per drain warp. Unit 0 up front, unit u + 1 at the start of
-    // this warp's pass over unit u: the drains of unit u - 1 are behind it, so the compute warps are past their wait on
-    // barrier (u + 1) & 1 for unit u - 1 (a barrier must never run two phases ahead of a waiter) and have read that
-    // buffer; the statistics are then ready a whole unit before they are needed.
-    auto row_stats = [&](int u) {
+    // Statistics of unit u -> buffer and barrier u & 1, 64 rows per drain warp. Unit 0 up front, unit u + 1 during this
+    // warp's pass over unit u: the drains of unit u - 1 are behind it, so the compute warps are past their wait on
+    // barrier (u + 1) & 1 for unit u - 1 (a barrier must never run two phases ahead of a waiter) and done with that
+    // buffer.
+    // (two passes of 32 rows; `last` publishes. Each pass is a global round trip: they are placed in the two gaps in
+    // which this warp waits for a key tile anyway.)
+    auto row_stats = [&](int u, int pass, bool last) {
       if (u >= n_units) return;
-      for (int r0 = q * 64; r0 < q * 64 + 64; r0 += 32)
-        if (r0 < R) row_stats_32(u, r0);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&stats_full[u & 1]);
+      const int r0 = q * 64 + pass * 32;
+      if (r0 < R) row_stats_32(u, r0);
+      if (last) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stats_full[u & 1]);
+      }
     };
-    row_stats(0);
+    row_stats(0, 0, false);
+    row_stats(0, 1, true);
     for (int u = 0; u < n_units; ++u) {
       const int w = (int)blockIdx.x + u * (int)gridDim.x;
       const int h = w % p.heads, n = w / p.heads;
-      row_stats(u + 1);
-      // rows of the tile start at sequence position seq0; column offset 0 q | D k | 2D v
+      row_stats(u + 1, 0, false);
+      if (NT == 1) row_stats(u + 1, 1, true);
+      // rows of the tile start at sequence position seq0; column offset 0 q | D k | 2D v. The 32 staged rows (128-byte
+      // swizzle, = the tensor map's) leave as ONE TMA store per warp and tile; rows beyond the sequence are clipped by
+      // the map. Lane 0 issues, commits and later waits for the store's shared-memory reads (bulk groups are per thread).
       auto drain = [&](uint32_t col, float sc, int seq0, int coff, uint64_t* release) {
         const int r0 = seq0 + q * 32;
         if (r0 < p.T) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous tile left the rows
+          __syncwarp();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t r[32];
@@ -1394,29 +1408,16 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
                            "r"(pack_bf16(__uint_as_float(r[8 * t + 6]) * sc, __uint_as_float(r[8 * t + 7]) * sc))
                            : "memory");
           }
+          fence_proxy_async();  // the staged rows are read by the TMA unit
         }
-        if (release) {  // the accumulator has been read: the MMAs that overwrite it may go while the rows are stored
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(release);
-        } else {
-          __syncwarp();
-        }
-        if (r0 < p.T) {
-#pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const int idx = lane + m * 32;
-            const int row = idx >> 3, ch = idx & 7;
-            if (r0 + row < p.T) {
-              uint4 v;
-              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                           : "r"(my + (uint32_t)row * 128u + (((uint32_t)ch ^ ((uint32_t)row & 7u)) << 4)));
-              *reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.T + r0 + row) * (3 * (size_t)D) + coff + h * HD +
-                                        ch * 8) = v;
-            }
+        if (release) tc_fence_before();  // the accumulator has been read: the MMAs that overwrite it may go
+        __syncwarp();
+        if (lane == 0) {
+          if (release) mbar_arrive(release);
+          if (r0 < p.T) {
+            tma_store_3d(&tmOut, my, coff + h * HD, r0, n);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          __syncwarp();  // the staging rows are rewritten by this warp's next tile
         }
       };
       for (int j = 0; j < NT; ++j) {
@@ -1434,11 +1435,13 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         if (j == NT - 1)
           for (int ii = 0; ii < NT; ++ii)
             drain(colDQ + (uint32_t)ii * 64u, p.scale, ii * 128, 0, ii == NT - 1 ? unit_free : nullptr);
+        if (j == 0 && NT == 2) row_stats(u + 1, 1, true);  // in the gap before the second key tile completes
 #ifdef MFK_TRACE2
         if (q == 0 && lane == 0) TRC(3);
 #endif
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
   } else if (warp >= TC_SOFTMAX_WARPS) {
     if (elect_one()) {
       const bool issuer_a = warp == TC_SOFTMAX_WARPS;  // A: TMA loads, S / dP, dQ.   B: dV, dK.
@@ -1778,11 +1781,14 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
     if ((rc = mfk_make_tmap_2d(&tmQkv2, qkv, 2, (uint64_t)rows, 3ull * D, 3ull * D, r2, 64, 128)) != MFK_OK) return rc;
     if ((rc = mfk_make_tmap_2d(&tmDo2, d_out, 2, (uint64_t)rows, (uint64_t)D, (uint64_t)D, r2, 64, 128)) != MFK_OK) return rc;
   }
+  CUtensorMap tmOut;
+  if ((rc = mfk_make_tmap_bf16_3d(&tmOut, dqkv, (uint64_t)N, (uint64_t)T, 3ull * D, 3ull * D, 32, 64)) != MFK_OK) return rc;
   const size_t smem = 4 * (size_t)p.R * 128 + 65536 + 16384 + 128 + 4096 + 1024;
   e = cudaFuncSetAttribute(attn_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int grid = p.total_units < g_attn_sms ? p.total_units : g_attn_sms;
-  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(FUSED_THREADS), smem, st, tmQkv, tmDo, tmQkv2, tmDo2, p);
+  const int rounds = (p.total_units + g_attn_sms - 1) / g_attn_sms;  // balanced grid, see mfk_attn_fwd_tc
+  const int grid = (p.total_units + rounds - 1) / rounds;
+  e = launch_pdl(attn_bwd_fused_tc_kernel, dim3(grid), dim3(FUSED_THREADS), smem, st, tmQkv, tmDo, tmQkv2, tmDo2, tmOut, p);
   if (e != cudaSuccess) return (int)e;
   return MFK_OK;
 }

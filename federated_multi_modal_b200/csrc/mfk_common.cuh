@@ -195,6 +195,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// 3-D store (columns, rows of a sequence, sequence): rows beyond the sequence length are clipped by the tensor map
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* src, int c0, int c1, uint64_t pol) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -344,3 +351,7 @@ int mfk_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uin
 // General form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 64 or 128 (= box_cols * elem_bytes).
 int mfk_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+// bf16 [seqs][rows][cols] with row stride ld_elems and sequence stride rows * ld_elems; box = box_rows x box_cols of ONE
+// sequence (a box never crosses into the next sequence: rows >= `rows` are clipped), 128-byte swizzle
+int mfk_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t seqs, uint64_t rows, uint64_t cols,
+                          uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);

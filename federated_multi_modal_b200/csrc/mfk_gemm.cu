@@ -787,6 +787,21 @@ int mfk_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_
   return r == CUDA_SUCCESS ? MFK_OK : MFK_EDRIVER;
 }
 
+int mfk_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t seqs, uint64_t rows, uint64_t cols,
+                          uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  int rc = load_encode();
+  if (rc != MFK_OK) return rc;
+  if (!mfk_aligned16(base) || (ld_elems * 2) % 16 != 0) return MFK_EALIGN;
+  cuuint64_t gdim[3] = {cols, rows, seqs};
+  cuuint64_t gstride[2] = {ld_elems * 2ull, rows * ld_elems * 2ull};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MFK_OK : MFK_EDRIVER;
+}
+
 static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
