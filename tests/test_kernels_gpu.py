@@ -175,6 +175,34 @@ def test_attention_fwd_bwd(N, T, heads, causal, impl):
     assert err < 3e-2 * max(1.0, x.grad.abs().max().item()), err
 
 
+@pytest.mark.parametrize("N,T,heads", [(3, 129, 2), (2, 144, 3), (2, 256, 2), (2, 128, 4), (20, 100, 8), (40, 199, 4),
+                                       (1, 200, 1), (2, 240, 2), (3, 33, 2)])
+def test_attention_fused_backward_edge_lengths(N, T, heads):
+    """Fused tcgen05 backward at the lengths where its operand-load schedule changes: one query / key tile (T <= 128) vs
+    two, second tiles of 16 .. 128 rows (loaded as short TMA boxes; the rows behind them alias the next buffer), several
+    units per CTA in both regimes (160 units on 148 SMs), and the 3-D TMA stores of dQ / dK / dV, which must clip at the
+    end of every sequence (the output buffer is NaN-filled first, and every row of it is compared)."""
+    D = heads * 64
+    qkv = rnd(N * T, 3 * D, dtype=BF16, seed=T)
+    out = torch.empty(N * T, D, device=DEV, dtype=BF16)
+    lse = torch.empty(N, heads, T, device=DEV, dtype=F32)
+    ops.attn_fwd(qkv, out, lse, N, T, heads, False, impl="tc")
+    x = qkv.float().requires_grad_(True)
+    o_ref, _, _ = _attn_ref(x, N, T, heads, False)
+    assert (out.float() - o_ref).abs().max().item() < 2e-2
+    d_out = rnd(N * T, D, dtype=BF16, seed=T + 1)
+    o_ref.backward(d_out.float())
+    delta = torch.empty(N * heads * T, device=DEV, dtype=F32)
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attn_bwd(qkv, out, d_out, lse, delta, dqkv, N, T, heads, False, impl="fused")
+    assert torch.isfinite(dqkv.float()).all()
+    err = (dqkv.float() - x.grad).abs().max().item()
+    assert err < 3e-2 * max(1.0, x.grad.abs().max().item()), err
+    d2 = torch.full_like(qkv, float("nan"))
+    ops.attn_bwd(qkv, out, d_out, lse, delta, d2, N, T, heads, False, impl="fused")
+    assert torch.equal(dqkv, d2)  # deterministic
+
+
 @pytest.mark.parametrize("N,T,heads,causal", [(4, 199, 12, False), (6, 10, 8, True), (3, 77, 8, True)])
 def test_attention_single_query_rows(N, T, heads, causal):
     """Last-block attention for one consumed row per sequence == the dense attention restricted to that row, forward
