@@ -1659,7 +1659,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
         // stage: those rows of P / dS are only ever read as the K tail that the second-stage MMAs skip (ks_last) or as
         // M rows whose results are discarded.
         const bool rows_live = i * 128 + q * 32 < p.T;
-#pragma unroll
+#pragma unroll 1  // (one copy of the two 32-column bodies: the unrolled pair cost instruction-fetch stalls, ncu stall_no_inst)
         for (int cc = 0; cc < 2; ++cc) {
           const int c = half * 32 + cc * 64;
           const int key0 = j * 128 + c;
