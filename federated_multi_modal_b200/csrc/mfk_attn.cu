@@ -1551,11 +1551,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
               mbar_wait(unit_free, ((uint32_t)u & 1u) ^ 1u);
               tc_fence_after();
             }
-#ifndef MFK_EXP_NO_DQ
             for (int ks = 0; ks < ks_j; ++ks)  // dQ_i += dS K_j        (K = keys of tile j: 2 column blocks x 4 k-steps)
-#else
-            for (int ks = 0; ks < 0; ++ks)
-#endif
               umma_bf16(tmem_base + colDQ + (uint32_t)i * 64u, dDsk + 1024ull * (ks >> 2) + 2ull * (ks & 3),
                         bk + 128ull * ks, idesc_kt, acc_j | (ks > 0));
             umma_commit(mma2_done);
@@ -1598,17 +1594,9 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
             const uint64_t bdo = dDom + 1024ull * i, bq = dQm + 1024ull * i;
             const uint32_t acc_i = i > 0;
             const int ks_i = i == NT - 1 ? ks_last : 8;
-#ifndef MFK_EXP_NO_DV
             for (int ks = 0; ks < ks_i; ++ks)  // dV_j += P^T dO_i   (K = query rows of tile i, 16 per MMA)
-#else
-            for (int ks = 0; ks < 0; ++ks)
-#endif
               umma_bf16(tmem_base + colDV, dPm + 128ull * ks, bdo + 128ull * ks, idesc_tt, acc_i | (ks > 0));
-#ifndef MFK_EXP_NO_DK
             for (int ks = 0; ks < ks_i; ++ks)  // dK_j += dS^T Q_i
-#else
-            for (int ks = 0; ks < 0; ++ks)
-#endif
               umma_bf16(tmem_base + colDK, dDsm + 128ull * ks, bq + 128ull * ks, idesc_tt, acc_i | (ks > 0));
             umma_commit(mma2_done);
             if (i == NT - 1) umma_commit(acc_done);

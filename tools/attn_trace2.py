@@ -22,6 +22,6 @@ t = buf.cpu().reshape(5, 64)
 base = int(t[0, 0])
 for i, nm in enumerate(["A (11/unit: start, landed, sdp, 4x(staged-ready, issued))", "compute w0 (wait, ready, [math0, released], staged)",
                         "B (per block: go, committed)", "drain q0 (per key tile: wait, acc_done seen, drained)",
-                        "compute w0 unit boundary (row_stats done, bar.sync passed)"]):
+                        "compute w0 unit boundary (last block staged, next unit statistics available)"]):
     print(nm)
     print("   ", [int(x) - base for x in t[i] if int(x) > 0])
