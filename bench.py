@@ -431,6 +431,11 @@ def fedavg_bitexact_check(ex, eng, dev, world):
         m32, m16, valid, _ = ex.reduce(rows, weighted=weighted)
         r32, r16 = fedavg_oracle(rows_cpu, [10.0 + k for k in range(len(rows_cpu))] if weighted else None)
         ok = ok and len(valid) == len(rows_cpu) and torch.equal(m32.cpu(), r32) and torch.equal(m16.cpu(), r16)
+        if world > 1:
+            # the sharded transport stores results straight into every peer's output buffers: a faster rank must not
+            # start the next reduce while a slower one is still copying this one's result to the host (a round of the
+            # trainer is ordered by its publish + status all-gather; two reduces in a row, as here, are not)
+            dist.barrier()
     chk = m32.double().sum().reshape(1).clone()
     flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
     same = True

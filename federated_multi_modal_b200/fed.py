@@ -160,7 +160,11 @@ class FedAvgExchange:
     def reduce(self, rows: Sequence[torch.Tensor], weighted: bool = False):
         """-> (mean fp32 [n], mean fp16 [n], valid client ids, per-client NaN/Inf flags[K]). Invalid clients
         (failed locally, or NaN/Inf in their tensors — check_weights_valid, trainers/maple_fed.py:271-277)
-        are excluded; the divisor is the number (or sample count) of the valid ones."""
+        are excluded; the divisor is the number (or sample count) of the valid ones.
+        The two means are the exchange's own output buffers, which the sharded transport fills by PEER stores: they stay
+        valid until any rank starts its next `reduce`. A round of the trainer is ordered by the next `gather()` (status
+        all-gather: every rank's earlier stream work, including its reads of the means, is complete before any rank gets
+        past it); code that calls `reduce` twice in a row must put a barrier between its reads and the second call."""
         from . import ops
         status = self.status.cpu()  # the one host synchronisation of the exchange
         bad = status[:, 2].to(torch.int32)  # validity scans ran on the owners' GPUs (gather)
