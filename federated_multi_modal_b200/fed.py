@@ -141,6 +141,7 @@ class FedAvgExchange:
 
     def gather(self) -> List[torch.Tensor]:
         """Returns the K client rows in client order (views; peer memory for the p2p transport)."""
+        self._reduced_since_gather = False
         self._scan_local()
         if self.world == 1:
             self.status.copy_(self.status_local)
@@ -162,9 +163,9 @@ class FedAvgExchange:
         (failed locally, or NaN/Inf in their tensors — check_weights_valid, trainers/maple_fed.py:271-277)
         are excluded; the divisor is the number (or sample count) of the valid ones.
         The two means are the exchange's own output buffers, which the sharded transport fills by PEER stores: they stay
-        valid until any rank starts its next `reduce`. A round of the trainer is ordered by the next `gather()` (status
-        all-gather: every rank's earlier stream work, including its reads of the means, is complete before any rank gets
-        past it); code that calls `reduce` twice in a row must put a barrier between its reads and the second call."""
+        valid until this rank calls `gather()` or `reduce` again. A round of the trainer is ordered by the next `gather()`
+        (status all-gather: every rank's earlier stream work, including its reads of the means, is complete before any
+        rank gets past it); a second `reduce` on the same rows starts with a symmetric-memory barrier for the same reason."""
         from . import ops
         status = self.status.cpu()  # the one host synchronisation of the exchange
         bad = status[:, 2].to(torch.int32)  # validity scans ran on the owners' GPUs (gather)
@@ -179,6 +180,12 @@ class FedAvgExchange:
             w, div = None, float(len(valid))
         if self._sharded is not None:
             sh = self._sharded
+            if getattr(self, "_reduced_since_gather", False):
+                # a second reduce on the same gathered rows: no status all-gather has ordered the peers' reads of the
+                # previous result (device copies or synchronous host copies made before this call) against the peer
+                # stores of this one, so every rank waits here until all of them have arrived
+                self._symm.barrier()
+            self._reduced_since_gather = True
             ops.fedavg_reduce_scatter(ptrs, w, div, len(valid), self.n, sh["lo"], sh["hi"], sh["p32"], sh["p16"],
                                       self.world)
         else:
