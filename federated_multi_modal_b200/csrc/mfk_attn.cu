@@ -1624,8 +1624,6 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     int trc4 = 0;
 #endif
     for (int u = 0; u < n_units; ++u) {
-      const int w = (int)blockIdx.x + u * (int)gridDim.x;
-      const int h = w % p.heads, n = w / p.heads;
       mbar_wait(&stats_full[u & 1], ((uint32_t)u >> 1) & 1u);  // row statistics of this unit are in smem (drain warps)
 #ifdef MFK_TRACE2
       if (p.trace && trc_me && trc4 < 60) p.trace[4 * 64 + trc4++] = clock64();
@@ -1748,7 +1746,6 @@ extern "C" int mfk_attn_bwd_fused(const void* qkv, const void* out, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = heads * HD;
   const long long rows = (long long)N * T;
-  const long long warps = rows * heads;
   cudaError_t e;
   (void)delta_ws;  // kept in the signature for symmetry with mfk_attn_bwd; delta is computed inside the kernel
   AttnBwdFusedParams p;
