@@ -1317,7 +1317,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid
     // ============================ drain warps: accumulators -> global ============================
     // A thread owns one TMEM lane (= row) of its warp's lane quarter; 32 lanes storing 128 bytes of 32 different
     // rows each would cost 32 memory wavefronts per instruction, so the bf16 rows are staged in the warp's own 4 KB
-    // (16-byte chunks XOR-swizzled by row) and leave as 4 whole 128-byte rows per instruction. Warp-local: no barrier
+    // (16-byte chunks XOR-swizzled by row = the 128-byte TMA swizzle) and leave as one TMA store. Warp-local: no barrier
     // with the other drain warps.
     const int q = warp & 3;
     const uint32_t x7 = (uint32_t)lane & 7u;
